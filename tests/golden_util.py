@@ -1,0 +1,28 @@
+"""Shared helpers for tests that use the reference-generated fixtures in tests/golden/."""
+import os
+
+import numpy as np
+import torch
+
+from wetts_b200 import synth
+from wetts_b200.hparams import builtin_config
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["v3_ragged", "v3_single", "v1_ragged", "v2_short"]
+
+
+def load_case(name):
+    d = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: d[k] for k in d.files}
+    hps = builtin_config(str(g["config"]))
+    sd = synth.make_state_dict(hps.model, int(g["n_vocab"]), int(g["n_speakers"]), seed=int(g["ckpt_seed"]))
+    fp = synth.fingerprint(sd)
+    assert abs(fp - float(g["fingerprint"])) <= 1e-9 * abs(fp), "synthetic checkpoint differs from the fixture's"
+    t = {k: torch.from_numpy(v) for k, v in g.items() if v.dtype.kind in "fi" and v.ndim > 0}
+    return hps, sd, g, t
+
+
+def rel_rms_err(a, b):
+    """max |a-b| relative to rms(b) -- the tolerance form SURVEY.md §8(c) states."""
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.pow(2).mean().sqrt().clamp_min(1e-30))
