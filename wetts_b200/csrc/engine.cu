@@ -1,0 +1,1070 @@
+// Host side of libwetts_b200: checkpoint ingestion, weight-norm folding, weight re-layout,
+// launch orchestration for every block of the VITS inference path, and the C ABI
+// declared in include/wetts_b200.h.  No CPU compute path exists here: every tensor
+// operation is a CUDA kernel from conv_kernels.cu / misc_kernels.cu.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wetts_b200.h"
+#include "kernels.cuh"
+
+namespace wetts {
+
+static thread_local std::string g_err;
+
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CUDA_OK(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct Raw {
+  float* d = nullptr;
+  std::vector<int64_t> dims;
+  size_t numel() const {
+    size_t n = 1;
+    for (auto v : dims) n *= (size_t)v;
+    return n;
+  }
+};
+
+struct Conv {
+  float* w = nullptr;
+  float* b = nullptr;
+  int Cin = 0, Cout = 0, CoutPad = 0, K = 1;
+};
+struct ConvT {
+  float* w = nullptr;
+  float* b = nullptr;
+  int Cin = 0, Cout = 0, CoutPad = 0, k = 0, u = 1, ntaps = 2, pad = 0;
+};
+struct Ln {
+  float* g = nullptr;
+  float* b = nullptr;
+  int C = 0;
+};
+struct Dds {
+  float* dww[3];
+  float* dwb[3];
+  Conv c1x1[3];
+  Ln n1[3], n2[3];
+};
+
+static int round_cout(int c) { return (c % 64 == 0) ? c : ((c + 31) / 32) * 32; }
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base;
+  size_t cap, off = 0;
+  bool dry;  // size query only
+  Arena(void* p, size_t c) : base((char*)p), cap(c), dry(p == nullptr) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* r = dry ? nullptr : (T*)(base + off);
+    off += n * sizeof(T);
+    return r;
+  }
+  bool ok() const { return dry || off <= cap; }
+};
+
+}  // namespace wetts
+
+using namespace wetts;
+
+struct wetts_vits_s {
+  wetts_vits_config cfg;
+  int device = 0;
+  bool finalized = false;
+  std::map<std::string, Raw> raw;
+  std::vector<void*> owned;
+  long long* host_pinned = nullptr;  // D2H landing zone for max(y_lengths)
+  long long* dev_scalar = nullptr;
+  unsigned long long launches_at_create = 0;
+  int U = 1;
+
+  // text encoder
+  float* emb = nullptr;
+  struct EncLayer {
+    Conv qkv, o, ffn1, ffn2;
+    float *rel_k = nullptr, *rel_v = nullptr;
+    Ln ln1, ln2;
+  };
+  std::vector<EncLayer> enc;
+  Conv proj_m, proj_logs;
+  // deterministic duration predictor
+  Conv dp_cond, dp_c1, dp_c2, dp_proj;
+  Ln dp_n1, dp_n2;
+  // stochastic duration predictor
+  Conv sdp_pre, sdp_proj, sdp_cond;
+  Dds sdp_dds;
+  struct ConvFlow {
+    float *pre_w = nullptr, *pre_b = nullptr;
+    Dds dds;
+    Conv proj;
+  } cf[3];  // flows 7, 5, 3 in application order
+  float *ea_m = nullptr, *ea_logs = nullptr;
+  // flow
+  struct Coupling {
+    Conv pre, post, cond, in[4], rs[4];
+    bool flipped = false;
+  } flow[4];  // application order: reference layers 6, 4, 2, 0
+  // generator
+  Conv conv_pre, dec_cond;
+  std::vector<ConvT> ups;
+  struct ResBlock {
+    std::vector<Conv> c1, c2;  // type 2 uses c1 only
+    std::vector<int> dil;
+    int k = 3;
+  };
+  std::vector<ResBlock> rbs;
+  float* conv_post_w = nullptr;
+  int c_last = 0;
+  float* emb_g = nullptr;
+
+  // ---------------------------------------------------------------- helpers
+  template <typename T>
+  int dalloc(T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 16);
+    if (e != cudaSuccess) return fail("cudaMalloc(%zu) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    owned.push_back(q);
+    *p = (T*)q;
+    return 0;
+  }
+  const Raw* find(const std::string& k) const {
+    auto it = raw.find(k);
+    return it == raw.end() ? nullptr : &it->second;
+  }
+  int need(const std::string& k, const Raw** out) const {
+    *out = find(k);
+    if (!*out) return fail("missing checkpoint tensor '%s'", k.c_str());
+    return 0;
+  }
+  // plain weight for `prefix` (folds weight_g/weight_v when that is what the checkpoint has)
+  int folded_weight(const std::string& prefix, Raw* out) {
+    if (const Raw* w = find(prefix + ".weight")) {
+      *out = *w;
+      return 0;
+    }
+    const Raw *g, *v;
+    if (need(prefix + ".weight_g", &g) || need(prefix + ".weight_v", &v)) return 1;
+    const int rows = (int)v->dims[0];
+    const int cols = (int)(v->numel() / rows);
+    if ((int)g->numel() != rows) return fail("%s.weight_g has %zu elements, expected %d", prefix.c_str(), g->numel(), rows);
+    float* f;
+    if (dalloc(&f, v->numel())) return 1;
+    launch_weight_norm_fold(v->d, g->d, f, rows, cols, 0);
+    out->d = f;
+    out->dims = v->dims;
+    return 0;
+  }
+  int upload_ints(const std::vector<int>& h, int** d) {
+    if (dalloc(d, h.size())) return 1;
+    CUDA_OK(cudaMemcpy(*d, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+    return 0;
+  }
+  // Conv1d weight [Cout][Cin][K] -> packed [Cin'][K][CoutPad]; co_map: packed out channel -> source
+  // out channel (empty: identity); ci_map: packed in channel -> source in channel (empty: identity)
+  int pack_conv_from(const Raw& w, const float* bias_src, std::vector<int> co_map, const std::vector<int>& ci_map,
+                     Conv* c) {
+    if (w.dims.size() != 3) return fail("conv weight must be 3-D");
+    const int src_cout = (int)w.dims[0], src_cin = (int)w.dims[1], K = (int)w.dims[2];
+    if (co_map.empty()) {
+      co_map.resize(src_cout);
+      for (int i = 0; i < src_cout; ++i) co_map[i] = i;
+    }
+    c->Cout = (int)co_map.size();
+    c->CoutPad = round_cout(c->Cout);
+    c->Cin = ci_map.empty() ? src_cin : (int)ci_map.size();
+    c->K = K;
+    co_map.resize(c->CoutPad, -1);
+    int *d_co = nullptr, *d_ci = nullptr;
+    if (upload_ints(co_map, &d_co)) return 1;
+    if (!ci_map.empty() && upload_ints(ci_map, &d_ci)) return 1;
+    if (dalloc(&c->w, (size_t)c->Cin * K * c->CoutPad)) return 1;
+    launch_pack_conv(w.d, c->w, d_co, d_ci, c->Cin, K, c->CoutPad, src_cin, 0);
+    c->b = nullptr;
+    if (bias_src) {
+      if (dalloc(&c->b, (size_t)c->CoutPad)) return 1;
+      launch_gather_vec(bias_src, c->b, d_co, c->CoutPad, 0);
+    }
+    return 0;
+  }
+  int make_conv(const std::string& prefix, Conv* c, bool bias = true, std::vector<int> co_map = {},
+                const std::vector<int>& ci_map = {}) {
+    Raw w;
+    if (folded_weight(prefix, &w)) return 1;
+    const float* bsrc = nullptr;
+    if (bias) {
+      const Raw* b;
+      if (need(prefix + ".bias", &b)) return 1;
+      bsrc = b->d;
+    }
+    return pack_conv_from(w, bsrc, co_map, ci_map, c);
+  }
+  int make_ln(const std::string& prefix, Ln* l) {
+    const Raw *g, *b;
+    if (need(prefix + ".gamma", &g) || need(prefix + ".beta", &b)) return 1;
+    l->g = g->d;
+    l->b = b->d;
+    l->C = (int)g->numel();
+    if (l->C > 256) return fail("LayerNorm over %d channels not supported (max 256)", l->C);
+    return 0;
+  }
+  int make_dds(const std::string& prefix, Dds* d) {
+    for (int i = 0; i < 3; ++i) {
+      const Raw *w, *b;
+      const std::string p = prefix + ".convs_sep." + std::to_string(i);
+      if (need(p + ".weight", &w) || need(p + ".bias", &b)) return 1;
+      if (w->dims.size() != 3 || w->dims[2] != 3) return fail("%s: depthwise kernel size must be 3", p.c_str());
+      d->dww[i] = w->d;
+      d->dwb[i] = b->d;
+      if (make_conv(prefix + ".convs_1x1." + std::to_string(i), &d->c1x1[i])) return 1;
+      if (make_ln(prefix + ".norms_1." + std::to_string(i), &d->n1[i])) return 1;
+      if (make_ln(prefix + ".norms_2." + std::to_string(i), &d->n2[i])) return 1;
+    }
+    return 0;
+  }
+};
+
+// ================================================================== block launch helpers
+namespace wetts {
+
+static ConvArgs conv_args(const Conv& c, const float* in, long long in_bs, int in_cs, int B, int T, int dil = 1) {
+  ConvArgs a;
+  a.in = in;
+  a.in_bs = in_bs;
+  a.in_cs = in_cs;
+  a.w = c.w;
+  a.bias = c.b;
+  a.B = B;
+  a.Cin = c.Cin;
+  a.Cout = c.Cout;
+  a.CoutPad = c.CoutPad;
+  a.T = T;
+  a.K = c.K;
+  a.dil = dil;
+  a.pad_left = (c.K - 1) * dil / 2;
+  a.ep.out_bs = (long long)c.Cout * T;
+  return a;
+}
+
+// per-(b, co) vector from g: out[b][co] = W g[b] + bias   (a Conv1d over T == 1)
+static void cond_vector(const Conv& c, const float* g, int B, float* out, cudaStream_t s) {
+  ConvArgs a = conv_args(c, g, c.Cin, 1, B, 1);
+  a.ep.out = out;
+  a.ep.out_bs = c.Cout;
+  launch_conv1d(a, s);
+}
+
+static void run_dds(const Dds& d, float* x, float* y, float* y2, const long long* lengths, int B, int C, int T,
+                    cudaStream_t s) {
+  // duration_predictors.py:45-57 (the caller applies the trailing `* x_mask` through in_mask of the next conv)
+  int dil = 1;
+  for (int i = 0; i < 3; ++i) {
+    LnArgs l;
+    l.a = x;
+    l.dww = d.dww[i];
+    l.dwb = d.dwb[i];
+    l.dil = dil;
+    l.gamma = d.n1[i].g;
+    l.beta = d.n1[i].b;
+    l.act = 1;
+    l.out = y;
+    l.lengths = lengths;
+    l.B = B;
+    l.C = C;
+    l.T = T;
+    launch_layernorm(l, s);
+    ConvArgs a = conv_args(d.c1x1[i], y, (long long)C * T, T, B, T);
+    a.ep.out = y2;
+    launch_conv1d(a, s);
+    LnArgs l2;
+    l2.a = y2;
+    l2.gamma = d.n2[i].g;
+    l2.beta = d.n2[i].b;
+    l2.act = 1;
+    l2.res = x;
+    l2.out = x;
+    l2.B = B;
+    l2.C = C;
+    l2.T = T;
+    launch_layernorm(l2, s);
+    dil *= 3;
+  }
+}
+
+}  // namespace wetts
+
+// ================================================================== C ABI
+extern "C" {
+
+const char* wetts_last_error(void) { return g_err.c_str(); }
+const char* wetts_version(void) { return "wetts_b200 0.1 (sm_100a, fp32 SIMT path)"; }
+
+int wetts_vits_create(const wetts_vits_config* cfg, int device, wetts_vits_t* out) {
+  if (!cfg || !out) return fail("null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("no CUDA device: wetts_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail("device %d out of range (have %d)", device, ndev);
+  CUDA_OK(cudaSetDevice(device));
+  const wetts_vits_config& c = *cfg;
+  if (c.hidden_channels % c.n_heads) return fail("hidden_channels %% n_heads != 0");
+  if (c.hidden_channels / c.n_heads > 96) return fail("head dim %d > 96 not supported", c.hidden_channels / c.n_heads);
+  if (c.hidden_channels > 256 || c.inter_channels % 2) return fail("unsupported channel configuration");
+  if (c.n_upsamples < 1 || c.n_upsamples > WETTS_MAX_UPSAMPLES) return fail("bad n_upsamples");
+  if (c.n_resblock_kernels < 1 || c.n_resblock_kernels > WETTS_MAX_RESBLOCK_KERNELS) return fail("bad n_resblock_kernels");
+  if (c.resblock_type != 1 && c.resblock_type != 2) return fail("resblock_type must be 1 or 2");
+  int U = 1;
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+    if (u < 1 || 32 % u) return fail("upsample rate %d must divide 32", u);
+    if (k % u || (k - u) % 2) return fail("upsample kernel %d incompatible with rate %d", k, u);
+    U *= u;
+  }
+  for (int j = 0; j < c.n_resblock_kernels; ++j) {
+    if (c.resblock_kernel_sizes[j] % 2 == 0) return fail("resblock kernel sizes must be odd");
+    if (c.resblock_n_dilations[j] < 1 || c.resblock_n_dilations[j] > WETTS_MAX_DILATIONS) return fail("bad dilation count");
+  }
+  if (c.kernel_size % 2 == 0) return fail("FFN kernel_size must be odd");
+  wetts_vits_s* h = new wetts_vits_s();
+  h->cfg = c;
+  h->device = device;
+  h->U = U;
+  h->launches_at_create = kernel_launch_counter();
+  if (cudaMallocHost((void**)&h->host_pinned, 64) != cudaSuccess || cudaMalloc((void**)&h->dev_scalar, 64) != cudaSuccess) {
+    delete h;
+    return fail("allocation failed");
+  }
+  *out = h;
+  return 0;
+}
+
+void wetts_vits_destroy(wetts_vits_t h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void* p : h->owned) cudaFree(p);
+  for (auto& kv : h->raw) cudaFree(kv.second.d);
+  if (h->host_pinned) cudaFreeHost(h->host_pinned);
+  if (h->dev_scalar) cudaFree(h->dev_scalar);
+  delete h;
+}
+
+int wetts_vits_upsample_factor(wetts_vits_t h) { return h ? h->U : 0; }
+uint64_t wetts_vits_launch_count(wetts_vits_t h) { return h ? kernel_launch_counter() - h->launches_at_create : 0; }
+
+int wetts_vits_set_tensor(wetts_vits_t h, const char* name, const void* data, const int64_t* dims, int ndim) {
+  if (!h || !name || !data || (!dims && ndim > 0)) return fail("null argument");
+  if (h->finalized) return fail("handle is finalized (immutable)");
+  if (!strncmp(name, "enc_q.", 6)) return 0;  // posterior encoder: never on the inference path
+  CUDA_OK(cudaSetDevice(h->device));
+  Raw r;
+  r.dims.assign(dims, dims + ndim);
+  for (auto d : r.dims)
+    if (d <= 0) return fail("tensor '%s' has a non-positive dimension", name);
+  const size_t n = r.numel();
+  CUDA_OK(cudaMalloc((void**)&r.d, n * sizeof(float) + 16));
+  cudaError_t e = cudaMemcpy(r.d, data, n * sizeof(float), cudaMemcpyDefault);
+  if (e != cudaSuccess) {
+    cudaFree(r.d);
+    return fail("copy of '%s' failed: %s", name, cudaGetErrorString(e));
+  }
+  auto it = h->raw.find(name);
+  if (it != h->raw.end()) cudaFree(it->second.d);
+  h->raw[name] = r;
+  return 0;
+}
+
+int wetts_vits_finalize(wetts_vits_t h) {
+  if (!h) return fail("null handle");
+  if (h->finalized) return 0;
+  CUDA_OK(cudaSetDevice(h->device));
+  const wetts_vits_config& c = h->cfg;
+  const int H = c.hidden_channels, Cc = c.inter_channels, half = Cc / 2, gin = c.gin_channels;
+  const Raw* r;
+  // ---- text encoder
+  if (h->need("enc_p.emb.weight", &r)) return 1;
+  if (r->dims.size() != 2 || r->dims[0] != c.n_vocab || r->dims[1] != H)
+    return fail("enc_p.emb.weight has shape [%lld,%lld], config says [%d,%d]", (long long)r->dims[0],
+                (long long)(r->dims.size() > 1 ? r->dims[1] : 0), c.n_vocab, H);
+  h->emb = r->d;
+  h->enc.resize(c.n_layers);
+  for (int i = 0; i < c.n_layers; ++i) {
+    auto& L = h->enc[i];
+    const std::string a = "enc_p.encoder.attn_layers." + std::to_string(i);
+    // q, k, v fused into one 1x1 conv with 3H output channels
+    Raw wq, wk, wv;
+    if (h->folded_weight(a + ".conv_q", &wq) || h->folded_weight(a + ".conv_k", &wk) || h->folded_weight(a + ".conv_v", &wv))
+      return 1;
+    const Raw *bq, *bk, *bv;
+    if (h->need(a + ".conv_q.bias", &bq) || h->need(a + ".conv_k.bias", &bk) || h->need(a + ".conv_v.bias", &bv)) return 1;
+    Raw cat;
+    cat.dims = {3 * H, H, 1};
+    float* catb;
+    if (h->dalloc(&cat.d, (size_t)3 * H * H) || h->dalloc(&catb, (size_t)3 * H)) return 1;
+    const Raw* ws[3] = {&wq, &wk, &wv};
+    const Raw* bs[3] = {bq, bk, bv};
+    for (int j = 0; j < 3; ++j) {
+      if ((int)ws[j]->numel() != H * H) return fail("%s: unexpected q/k/v weight size", a.c_str());
+      CUDA_OK(cudaMemcpy(cat.d + (size_t)j * H * H, ws[j]->d, sizeof(float) * H * H, cudaMemcpyDeviceToDevice));
+      CUDA_OK(cudaMemcpy(catb + (size_t)j * H, bs[j]->d, sizeof(float) * H, cudaMemcpyDeviceToDevice));
+    }
+    if (h->pack_conv_from(cat, catb, {}, {}, &L.qkv)) return 1;
+    if (h->make_conv(a + ".conv_o", &L.o)) return 1;
+    if (h->need(a + ".emb_rel_k", &r)) return 1;
+    if (r->dims.size() != 3 || r->dims[0] != 1 || r->dims[1] != 9 || r->dims[2] != H / c.n_heads)
+      return fail("%s.emb_rel_k: only shared-head window-4 tables are supported", a.c_str());
+    L.rel_k = r->d;
+    if (h->need(a + ".emb_rel_v", &r)) return 1;
+    L.rel_v = r->d;
+    if (h->make_ln("enc_p.encoder.norm_layers_1." + std::to_string(i), &L.ln1)) return 1;
+    if (h->make_ln("enc_p.encoder.norm_layers_2." + std::to_string(i), &L.ln2)) return 1;
+    if (h->make_conv("enc_p.encoder.ffn_layers." + std::to_string(i) + ".conv_1", &L.ffn1)) return 1;
+    if (h->make_conv("enc_p.encoder.ffn_layers." + std::to_string(i) + ".conv_2", &L.ffn2)) return 1;
+  }
+  {
+    std::vector<int> lo(Cc), hi(Cc);
+    for (int i = 0; i < Cc; ++i) { lo[i] = i; hi[i] = Cc + i; }
+    if (h->make_conv("enc_p.proj", &h->proj_m, true, lo) || h->make_conv("enc_p.proj", &h->proj_logs, true, hi)) return 1;
+  }
+  // ---- duration predictor
+  if (c.use_sdp) {
+    if (h->make_conv("dp.pre", &h->sdp_pre) || h->make_conv("dp.proj", &h->sdp_proj)) return 1;
+    if (gin && h->make_conv("dp.cond", &h->sdp_cond)) return 1;
+    if (h->make_dds("dp.convs", &h->sdp_dds)) return 1;
+    const int order[3] = {7, 5, 3};
+    for (int j = 0; j < 3; ++j) {
+      const std::string p = "dp.flows." + std::to_string(order[j]);
+      const Raw *pw, *pb;
+      if (h->need(p + ".pre.weight", &pw) || h->need(p + ".pre.bias", &pb)) return 1;
+      h->cf[j].pre_w = pw->d;
+      h->cf[j].pre_b = pb->d;
+      if (h->make_dds(p + ".convs", &h->cf[j].dds)) return 1;
+      if (h->make_conv(p + ".proj", &h->cf[j].proj)) return 1;
+      if (h->cf[j].proj.Cout != 29) return fail("%s.proj must have 29 output channels (10 bins)", p.c_str());
+    }
+    const Raw *m, *ls;
+    if (h->need("dp.flows.0.m", &m) || h->need("dp.flows.0.logs", &ls)) return 1;
+    h->ea_m = m->d;
+    h->ea_logs = ls->d;
+  } else {
+    if (gin && h->make_conv("dp.cond", &h->dp_cond)) return 1;
+    if (h->make_conv("dp.conv_1", &h->dp_c1) || h->make_conv("dp.conv_2", &h->dp_c2) || h->make_conv("dp.proj", &h->dp_proj))
+      return 1;
+    if (h->make_ln("dp.norm_1", &h->dp_n1) || h->make_ln("dp.norm_2", &h->dp_n2)) return 1;
+  }
+  // ---- flow (application order 6,4,2,0; odd number of preceding Flips => channels reversed)
+  {
+    const int order[4] = {6, 4, 2, 0};
+    std::vector<int> gate(2 * H);
+    for (int p = 0; p < 2 * H; ++p) gate[p] = (p & 1) ? H + (p >> 1) : (p >> 1);
+    for (int j = 0; j < 4; ++j) {
+      auto& F = h->flow[j];
+      F.flipped = (j % 2 == 0);
+      const std::string p = "flow.flows." + std::to_string(order[j]);
+      std::vector<int> ci;
+      if (F.flipped) {
+        ci.resize(half);
+        for (int q = 0; q < half; ++q) ci[q] = half - 1 - q;
+      }
+      if (h->make_conv(p + ".pre", &F.pre, true, {}, ci)) return 1;
+      if (h->make_conv(p + ".post", &F.post)) return 1;
+      if (F.post.Cout != half) return fail("%s.post: only mean_only couplings are supported", p.c_str());
+      if (gin && h->make_conv(p + ".enc.cond_layer", &F.cond)) return 1;
+      for (int i = 0; i < 4; ++i) {
+        if (h->make_conv(p + ".enc.in_layers." + std::to_string(i), &F.in[i], true, gate)) return 1;
+        if (F.in[i].K != 5) return fail("%s: WN kernel size must be 5", p.c_str());
+        if (h->make_conv(p + ".enc.res_skip_layers." + std::to_string(i), &F.rs[i])) return 1;
+      }
+    }
+  }
+  // ---- generator
+  {
+    if (h->make_conv("dec.conv_pre", &h->conv_pre)) return 1;
+    if (gin && h->make_conv("dec.cond", &h->dec_cond)) return 1;
+    int ch = c.upsample_initial_channel;
+    h->ups.resize(c.n_upsamples);
+    for (int i = 0; i < c.n_upsamples; ++i) {
+      const std::string p = "dec.ups." + std::to_string(i);
+      Raw w;
+      if (h->folded_weight(p, &w)) return 1;
+      const Raw* b;
+      if (h->need(p + ".bias", &b)) return 1;
+      ConvT& t = h->ups[i];
+      t.Cin = (int)w.dims[0];
+      t.Cout = (int)w.dims[1];
+      t.k = (int)w.dims[2];
+      t.u = c.upsample_rates[i];
+      if (t.Cin != ch || t.k != c.upsample_kernel_sizes[i]) return fail("%s: shape does not match the config", p.c_str());
+      t.ntaps = t.k / t.u;
+      t.pad = (t.k - t.u) / 2;
+      t.CoutPad = round_cout(t.Cout);
+      if (h->dalloc(&t.w, (size_t)t.Cin * t.ntaps * t.CoutPad * t.u)) return 1;
+      launch_pack_convT(w.d, t.w, t.Cin, t.Cout, t.CoutPad, t.k, t.u, 0);
+      std::vector<int> idm(t.CoutPad, -1);
+      for (int q = 0; q < t.Cout; ++q) idm[q] = q;
+      int* dmap;
+      if (h->upload_ints(idm, &dmap) || h->dalloc(&t.b, (size_t)t.CoutPad)) return 1;
+      launch_gather_vec(b->d, t.b, dmap, t.CoutPad, 0);
+      ch = t.Cout;
+      for (int j = 0; j < c.n_resblock_kernels; ++j) {
+        wetts_vits_s::ResBlock rb;
+        rb.k = c.resblock_kernel_sizes[j];
+        const std::string rp = "dec.resblocks." + std::to_string(i * c.n_resblock_kernels + j);
+        for (int n = 0; n < c.resblock_n_dilations[j]; ++n) {
+          rb.dil.push_back(c.resblock_dilations[j][n]);
+          Conv a, bq;
+          if (c.resblock_type == 1) {
+            if (h->make_conv(rp + ".convs1." + std::to_string(n), &a) || h->make_conv(rp + ".convs2." + std::to_string(n), &bq))
+              return 1;
+            rb.c1.push_back(a);
+            rb.c2.push_back(bq);
+          } else {
+            if (h->make_conv(rp + ".convs." + std::to_string(n), &a)) return 1;
+            rb.c1.push_back(a);
+          }
+          if (a.K != rb.k || a.Cin != ch) return fail("%s: shape does not match the config", rp.c_str());
+        }
+        h->rbs.push_back(rb);
+      }
+    }
+    h->c_last = ch;
+    if (h->need("dec.conv_post.weight", &r)) return 1;
+    if (r->dims.size() != 3 || r->dims[0] != 1 || r->dims[1] != ch) return fail("dec.conv_post.weight: unexpected shape");
+    h->conv_post_w = r->d;
+  }
+  if (c.n_speakers > 0) {
+    if (h->need("emb_g.weight", &r)) return 1;
+    if (r->dims.size() != 2 || r->dims[0] != c.n_speakers || r->dims[1] != gin) return fail("emb_g.weight: unexpected shape");
+    h->emb_g = r->d;
+  }
+  CUDA_OK(cudaDeviceSynchronize());
+  CUDA_OK(cudaGetLastError());
+  h->finalized = true;
+  return 0;
+}
+
+#define CHECK_READY(h)                                     \
+  if (!(h)) return fail("null handle");                    \
+  if (!(h)->finalized) return fail("handle not finalized"); \
+  CUDA_OK(cudaSetDevice((h)->device));
+
+#define CHECK_LAUNCH() CUDA_OK(cudaGetLastError())
+
+// ------------------------------------------------------------------ speaker embedding
+int wetts_speaker_embedding(wetts_vits_t h, const int64_t* sid, int B, float* g, void* stream) {
+  CHECK_READY(h);
+  if (!h->emb_g) return fail("model has no speaker embedding (n_speakers == 0)");
+  launch_speaker_embed((const long long*)sid, h->emb_g, g, B, h->cfg.gin_channels, h->cfg.n_speakers, (cudaStream_t)stream);
+  CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ text encoder
+struct TextEncWs {
+  float *qkv, *att, *y, *f;
+};
+static size_t text_enc_layout(const wetts_vits_config& c, int B, int Tx, Arena& A, TextEncWs* w) {
+  const size_t H = c.hidden_channels, F = c.filter_channels, n = (size_t)B * Tx;
+  w->qkv = A.take<float>(3 * H * n);
+  w->att = A.take<float>(H * n);
+  w->y = A.take<float>(H * n);
+  w->f = A.take<float>(F * n);
+  return A.off;
+}
+size_t wetts_text_encoder_workspace_bytes(wetts_vits_t h, int B, int Tx) {
+  if (!h) return 0;
+  Arena A(nullptr, 0);
+  TextEncWs w;
+  return text_enc_layout(h->cfg, B, Tx, A, &w) + 256;
+}
+int wetts_text_encoder_forward(wetts_vits_t h, const int64_t* ids, const int64_t* lengths, int B, int Tx, float* h_out,
+                               float* m_out, float* logs_out, void* workspace, size_t workspace_bytes, void* stream) {
+  CHECK_READY(h);
+  if (B <= 0 || Tx <= 0) return fail("empty batch");
+  if (Tx > 3000) return fail("Tx=%d exceeds the attention kernel limit (3000)", Tx);
+  const wetts_vits_config& c = h->cfg;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena A(workspace, workspace_bytes);
+  TextEncWs w;
+  text_enc_layout(c, B, Tx, A, &w);
+  if (!workspace || !A.ok()) return fail("text encoder workspace too small: need %zu bytes", A.off);
+  const int H = c.hidden_channels, F = c.filter_channels;
+  const long long* len = (const long long*)lengths;
+  float* x = h_out;
+  launch_embed((const long long*)ids, len, h->emb, x, B, Tx, H, c.n_vocab, sqrtf((float)H), s);
+  for (int i = 0; i < c.n_layers; ++i) {
+    auto& L = h->enc[i];
+    ConvArgs a = conv_args(L.qkv, x, (long long)H * Tx, Tx, B, Tx);
+    a.ep.out = w.qkv;
+    launch_conv1d(a, s);
+    launch_rel_attention(w.qkv, L.rel_k, L.rel_v, len, w.att, B, H, Tx, c.n_heads, 4, s);
+    a = conv_args(L.o, w.att, (long long)H * Tx, Tx, B, Tx);
+    a.ep.out = w.y;
+    launch_conv1d(a, s);
+    LnArgs l;
+    l.a = x; l.b = w.y; l.gamma = L.ln1.g; l.beta = L.ln1.b; l.out = x; l.B = B; l.C = H; l.T = Tx;
+    launch_layernorm(l, s);
+    a = conv_args(L.ffn1, x, (long long)H * Tx, Tx, B, Tx);
+    a.lengths = len; a.in_mask = 1; a.ep.act = 1; a.ep.out = w.f;
+    launch_conv1d(a, s);
+    a = conv_args(L.ffn2, w.f, (long long)F * Tx, Tx, B, Tx);
+    a.lengths = len; a.in_mask = 1; a.ep.out_mask = 1; a.ep.out = w.y;
+    launch_conv1d(a, s);
+    LnArgs l2;
+    l2.a = x; l2.b = w.y; l2.gamma = L.ln2.g; l2.beta = L.ln2.b; l2.out = x; l2.B = B; l2.C = H; l2.T = Tx;
+    l2.lengths = len; l2.out_mask = (i == c.n_layers - 1);
+    launch_layernorm(l2, s);
+  }
+  ConvArgs a = conv_args(h->proj_m, x, (long long)H * Tx, Tx, B, Tx);
+  a.lengths = len; a.ep.out_mask = 1; a.ep.out = m_out;
+  launch_conv1d(a, s);
+  a = conv_args(h->proj_logs, x, (long long)H * Tx, Tx, B, Tx);
+  a.lengths = len; a.ep.out_mask = 1; a.ep.out = logs_out;
+  launch_conv1d(a, s);
+  CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ duration predictors
+struct DurWs {
+  float *cvec, *x, *y, *y2, *xc, *hb, *u, *z0, *z1;
+};
+static size_t dur_layout(const wetts_vits_config& c, int B, int Tx, Arena& A, DurWs* w) {
+  const size_t n = (size_t)B * Tx;
+  if (c.use_sdp) {
+    const size_t H = c.hidden_channels;
+    w->cvec = A.take<float>((size_t)B * H);
+    w->x = A.take<float>(H * n);
+    w->y = A.take<float>(H * n);
+    w->y2 = A.take<float>(H * n);
+    w->xc = A.take<float>(H * n);
+    w->hb = A.take<float>(H * n);
+    w->u = A.take<float>(29 * n);
+    w->z0 = A.take<float>(2 * n);
+    w->z1 = A.take<float>(2 * n);
+  } else {
+    w->cvec = A.take<float>((size_t)B * c.hidden_channels);
+    w->x = A.take<float>((size_t)c.hidden_channels * n);
+    w->y = A.take<float>(256 * n);
+    w->y2 = A.take<float>(256 * n);
+    w->xc = w->hb = w->u = w->z0 = w->z1 = nullptr;
+  }
+  return A.off;
+}
+size_t wetts_duration_workspace_bytes(wetts_vits_t h, int B, int Tx) {
+  if (!h) return 0;
+  Arena A(nullptr, 0);
+  DurWs w;
+  return dur_layout(h->cfg, B, Tx, A, &w) + 256;
+}
+}  // extern "C"
+
+namespace wetts {
+__global__ void add_channel_vec_kernel(const float* __restrict__ in, const float* __restrict__ vec, float* __restrict__ out,
+                                       int C, int T) {
+  const int b = blockIdx.z, c = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < T) {
+    const long long o = ((long long)b * C + c) * T + t;
+    out[o] = in[o] + vec[(long long)b * C + c];
+  }
+}
+}  // namespace wetts
+
+extern "C" {
+int wetts_duration_forward(wetts_vits_t h, const float* h_in, const int64_t* lengths, const float* g, const float* noise_w,
+                           float noise_scale_w, int B, int Tx, float* logw, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  CHECK_READY(h);
+  const wetts_vits_config& c = h->cfg;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena A(workspace, workspace_bytes);
+  DurWs w;
+  dur_layout(c, B, Tx, A, &w);
+  if (!workspace || !A.ok()) return fail("duration workspace too small: need %zu bytes", A.off);
+  const int H = c.hidden_channels;
+  const long long* len = (const long long*)lengths;
+  const bool has_g = g && c.gin_channels > 0;
+  if (!c.use_sdp) {
+    const float* x = h_in;
+    if (has_g) {
+      cond_vector(h->dp_cond, g, B, w.cvec, s);
+      dim3 grid((Tx + 127) / 128, H, B);
+      add_channel_vec_kernel<<<grid, 128, 0, s>>>(h_in, w.cvec, w.x, H, Tx);
+      count_launch();
+      x = w.x;
+    }
+    ConvArgs a = conv_args(h->dp_c1, x, (long long)H * Tx, Tx, B, Tx);
+    a.lengths = len; a.in_mask = 1; a.ep.act = 1; a.ep.out = w.y;
+    launch_conv1d(a, s);
+    LnArgs l;
+    l.a = w.y; l.gamma = h->dp_n1.g; l.beta = h->dp_n1.b; l.out = w.y; l.B = B; l.C = h->dp_n1.C; l.T = Tx;
+    launch_layernorm(l, s);
+    a = conv_args(h->dp_c2, w.y, (long long)h->dp_c1.Cout * Tx, Tx, B, Tx);
+    a.lengths = len; a.in_mask = 1; a.ep.act = 1; a.ep.out = w.y2;
+    launch_conv1d(a, s);
+    l.a = w.y2; l.gamma = h->dp_n2.g; l.beta = h->dp_n2.b; l.out = w.y2; l.C = h->dp_n2.C;
+    launch_layernorm(l, s);
+    a = conv_args(h->dp_proj, w.y2, (long long)h->dp_c2.Cout * Tx, Tx, B, Tx);
+    a.lengths = len; a.in_mask = 1; a.ep.out_mask = 1; a.ep.out = logw;
+    launch_conv1d(a, s);
+    CHECK_LAUNCH();
+    return 0;
+  }
+  if (!noise_w) return fail("stochastic duration predictor needs noise_w [B,2,Tx]");
+  // x = pre(h) + cond(g)
+  ConvArgs a = conv_args(h->sdp_pre, h_in, (long long)H * Tx, Tx, B, Tx);
+  if (has_g) {
+    cond_vector(h->sdp_cond, g, B, w.cvec, s);
+    a.ep.cond = w.cvec;
+    a.ep.cond_bs = H;
+  }
+  a.ep.out = w.x;
+  launch_conv1d(a, s);
+  run_dds(h->sdp_dds, w.x, w.y, w.y2, len, B, H, Tx, s);
+  a = conv_args(h->sdp_proj, w.x, (long long)H * Tx, Tx, B, Tx);
+  a.lengths = len; a.in_mask = 1; a.ep.out_mask = 1; a.ep.out = w.xc;
+  launch_conv1d(a, s);
+  launch_scale(noise_w, w.z0, noise_scale_w, (long long)B * 2 * Tx, s);
+  float *zc = w.z0, *zn = w.z1;
+  for (int j = 0; j < 3; ++j) {
+    auto& F = h->cf[j];
+    launch_convflow_pre(zc, 1, F.pre_w, F.pre_b, w.xc, w.hb, B, H, Tx, s);
+    run_dds(F.dds, w.hb, w.y, w.y2, len, B, H, Tx, s);
+    a = conv_args(F.proj, w.hb, (long long)H * Tx, Tx, B, Tx);
+    a.lengths = len; a.in_mask = 1; a.ep.out_mask = 1; a.ep.out = w.u;
+    launch_conv1d(a, s);
+    launch_spline_flip(zc, w.u, 29, zn, len, B, Tx, 1.f / sqrtf((float)H), s);
+    float* t = zc; zc = zn; zn = t;
+  }
+  launch_sdp_final(zc, h->ea_m, h->ea_logs, len, logw, B, Tx, s);
+  CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ length regulation / prior expansion
+int wetts_length_regulate(wetts_vits_t h, const float* logw, const int64_t* x_lengths, const float* durations,
+                          float length_scale, int B, int Tx, float* w_ceil, int32_t* cum, int64_t* y_lengths, void* stream) {
+  CHECK_READY(h);
+  launch_length_regulate(logw, (const long long*)x_lengths, durations, length_scale, B, Tx, w_ceil, cum,
+                         (long long*)y_lengths, (cudaStream_t)stream);
+  CHECK_LAUNCH();
+  return 0;
+}
+
+int wetts_expand_prior(wetts_vits_t h, const float* m, const float* logs, const int32_t* cum, const int64_t* x_lengths,
+                       const int64_t* y_lengths, const float* noise_z, int64_t noise_bs, int64_t noise_rs,
+                       float noise_scale, int B, int Tx, int Ty, float* m_p_out, float* logs_p_out, float* z_p_out,
+                       float* attn, float* y_mask, void* stream) {
+  CHECK_READY(h);
+  if (z_p_out && !noise_z) return fail("z_p requested without noise_z");
+  launch_expand_prior(m, logs, cum, (const long long*)x_lengths, (const long long*)y_lengths, noise_z, noise_bs, noise_rs,
+                      noise_scale, B, h->cfg.inter_channels, Tx, Ty, m_p_out, logs_p_out, z_p_out, attn, y_mask,
+                      (cudaStream_t)stream);
+  CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ flow
+struct FlowWs {
+  float *gc, *hb, *acts, *skip;
+};
+static size_t flow_layout(const wetts_vits_config& c, int B, int Ty, Arena& A, FlowWs* w) {
+  const size_t H = c.hidden_channels, n = (size_t)B * Ty;
+  w->gc = A.take<float>((size_t)B * 8 * H);
+  w->hb = A.take<float>(H * n);
+  w->acts = A.take<float>(H * n);
+  w->skip = A.take<float>(H * n);
+  return A.off;
+}
+size_t wetts_flow_workspace_bytes(wetts_vits_t h, int B, int Ty) {
+  if (!h) return 0;
+  Arena A(nullptr, 0);
+  FlowWs w;
+  return flow_layout(h->cfg, B, Ty, A, &w) + 256;
+}
+int wetts_flow_reverse(wetts_vits_t h, float* z, const int64_t* y_lengths, const float* g, int B, int Ty, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  CHECK_READY(h);
+  const wetts_vits_config& c = h->cfg;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena A(workspace, workspace_bytes);
+  FlowWs w;
+  flow_layout(c, B, Ty, A, &w);
+  if (!workspace || !A.ok()) return fail("flow workspace too small: need %zu bytes", A.off);
+  const int H = c.hidden_channels, Cc = c.inter_channels, half = Cc / 2;
+  const long long* len = (const long long*)y_lengths;
+  const bool has_g = g && c.gin_channels > 0;
+  for (int j = 0; j < 4; ++j) {
+    auto& F = h->flow[j];
+    if (has_g) cond_vector(F.cond, g, B, w.gc, s);
+    // h = pre(x0) * mask
+    ConvArgs a = conv_args(F.pre, z + (F.flipped ? (long long)half * Ty : 0), (long long)Cc * Ty, Ty, B, Ty);
+    a.lengths = len; a.ep.out_mask = 1; a.ep.out = w.hb;
+    launch_conv1d(a, s);
+    for (int i = 0; i < 4; ++i) {
+      a = conv_args(F.in[i], w.hb, (long long)H * Ty, Ty, B, Ty);
+      a.ep.mode = EPI_GATE; a.ep.H = H; a.ep.out = w.acts; a.ep.out_bs = (long long)H * Ty;
+      if (has_g) { a.ep.cond = w.gc; a.ep.cond_bs = 8 * H; a.ep.cond_off = 2 * H * i; }
+      launch_conv1d(a, s);
+      a = conv_args(F.rs[i], w.acts, (long long)H * Ty, Ty, B, Ty);
+      a.lengths = len;
+      a.ep.mode = EPI_RES_SKIP; a.ep.H = H; a.ep.x = w.hb; a.ep.skip = w.skip; a.ep.out_bs = (long long)H * Ty;
+      a.ep.skip_init = (i == 0); a.ep.last = (i == 3);
+      launch_conv1d(a, s);
+    }
+    // m = post(out * mask) * mask ; x1 = (x1 - m) * mask
+    a = conv_args(F.post, w.skip, (long long)H * Ty, Ty, B, Ty);
+    a.lengths = len; a.in_mask = 1;
+    a.ep.mode = EPI_COUPLING; a.ep.out = z; a.ep.out_bs = (long long)Cc * Ty;
+    a.ep.z_c0 = F.flipped ? half - 1 : half;
+    a.ep.z_cstep = F.flipped ? -1 : 1;
+    launch_conv1d(a, s);
+  }
+  CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ generator
+struct GenWs {
+  float *cvec, *x[2], *xu, *r, *t;
+};
+static size_t gen_layout(wetts_vits_t h, int B, int T, Arena& A, GenWs* w) {
+  const wetts_vits_config& c = h->cfg;
+  size_t mx = (size_t)c.upsample_initial_channel * T;
+  size_t ch = c.upsample_initial_channel, len = T;
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    ch /= 2;
+    len *= c.upsample_rates[i];
+    if (ch * len > mx) mx = ch * len;
+  }
+  mx *= (size_t)B;
+  w->cvec = A.take<float>((size_t)B * c.upsample_initial_channel);
+  w->x[0] = A.take<float>(mx);
+  w->x[1] = A.take<float>(mx);
+  w->xu = A.take<float>(mx);
+  w->r = A.take<float>(mx);
+  w->t = c.resblock_type == 1 ? A.take<float>(mx) : nullptr;
+  return A.off;
+}
+size_t wetts_generator_workspace_bytes(wetts_vits_t h, int B, int T) {
+  if (!h) return 0;
+  Arena A(nullptr, 0);
+  GenWs w;
+  return gen_layout(h, B, T, A, &w) + 256;
+}
+int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_lengths, const float* g, int B, int T,
+                            float* audio, void* workspace, size_t workspace_bytes, void* stream) {
+  CHECK_READY(h);
+  if (B <= 0 || T <= 0) return fail("empty batch");
+  const wetts_vits_config& c = h->cfg;
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena A(workspace, workspace_bytes);
+  GenWs w;
+  gen_layout(h, B, T, A, &w);
+  if (!workspace || !A.ok()) return fail("generator workspace too small: need %zu bytes", A.off);
+  const int Cc = c.inter_channels;
+  const bool has_g = g && c.gin_channels > 0;
+  ConvArgs a = conv_args(h->conv_pre, z, (long long)Cc * T, T, B, T);
+  if (y_lengths) { a.lengths = (const long long*)y_lengths; a.in_mask = 1; }
+  if (has_g) {
+    cond_vector(h->dec_cond, g, B, w.cvec, s);
+    a.ep.cond = w.cvec;
+    a.ep.cond_bs = c.upsample_initial_channel;
+  }
+  int cur = 0;
+  a.ep.out = w.x[cur];
+  launch_conv1d(a, s);
+  int len = T;
+  const int nk = c.n_resblock_kernels;
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    const ConvT& up = h->ups[i];
+    ConvTArgs ta;
+    ta.in = w.x[cur]; ta.w = up.w; ta.bias = up.b; ta.out = w.xu; ta.B = B; ta.Cin = up.Cin; ta.Cout = up.Cout;
+    ta.CoutPad = up.CoutPad; ta.T = len; ta.u = up.u; ta.ntaps = up.ntaps; ta.pad = up.pad; ta.pre_slope = 0.1f;
+    launch_conv_transpose1d(ta, s);
+    len *= up.u;
+    const int ch = up.Cout;
+    const long long bs = (long long)ch * len;
+    float* acc = w.x[cur ^ 1];
+    for (int j = 0; j < nk; ++j) {
+      const auto& rb = h->rbs[i * nk + j];
+      const int nd = (int)rb.dil.size();
+      const int acc_mode = (nk == 1) ? 0 : (j == 0 ? 0 : (j < nk - 1 ? 1 : 2));
+      const float* curp = w.xu;
+      for (int n = 0; n < nd; ++n) {
+        const bool last = (n == nd - 1);
+        if (c.resblock_type == 1) {
+          ConvArgs c1 = conv_args(rb.c1[n], curp, bs, len, B, len, rb.dil[n]);
+          c1.pre_act = 1; c1.pre_slope = 0.1f; c1.ep.out = w.t;
+          launch_conv1d(c1, s);
+          ConvArgs c2 = conv_args(rb.c2[n], w.t, bs, len, B, len, 1);
+          c2.pre_act = 1; c2.pre_slope = 0.1f; c2.ep.resid = curp;
+          if (last) { c2.ep.mode = EPI_MRF; c2.ep.acc_mode = acc_mode; c2.ep.div = (float)nk; c2.ep.out = acc; }
+          else { c2.ep.mode = EPI_RESID; c2.ep.out = w.r; }
+          launch_conv1d(c2, s);
+          curp = w.r;
+        } else {
+          // ResBlock2: x = x + c(lrelu(x)); intermediates ping-pong between r and t-less buffers
+          ConvArgs c1 = conv_args(rb.c1[n], curp, bs, len, B, len, rb.dil[n]);
+          c1.pre_act = 1; c1.pre_slope = 0.1f; c1.ep.resid = curp;
+          float* dst = (curp == w.r) ? nullptr : w.r;
+          if (last) { c1.ep.mode = EPI_MRF; c1.ep.acc_mode = acc_mode; c1.ep.div = (float)nk; c1.ep.out = acc; }
+          else {
+            if (!dst) return fail("ResBlock2 with more than 2 dilations is not supported");
+            c1.ep.mode = EPI_RESID; c1.ep.out = dst;
+          }
+          launch_conv1d(c1, s);
+          curp = w.r;
+        }
+      }
+    }
+    cur ^= 1;
+  }
+  launch_conv_post_tanh(w.x[cur], h->conv_post_w, audio, B, h->c_last, len, 7, 0.01f, s);
+  CHECK_LAUNCH();
+  return 0;
+}
+
+// ------------------------------------------------------------------ whole path
+struct InferWs {
+  float *g, *hbuf, *m, *logs, *logw, *w_ceil, *zbuf;
+  int* cum;
+  void* scratch;
+  size_t scratch_bytes;
+};
+static size_t infer_layout(wetts_vits_t h, int B, int Tx, int max_frames, Arena& A, InferWs* w) {
+  const wetts_vits_config& c = h->cfg;
+  const size_t n = (size_t)B * Tx;
+  w->g = A.take<float>((size_t)B * (c.gin_channels > 0 ? c.gin_channels : 1));
+  w->hbuf = A.take<float>((size_t)c.hidden_channels * n);
+  w->m = A.take<float>((size_t)c.inter_channels * n);
+  w->logs = A.take<float>((size_t)c.inter_channels * n);
+  w->logw = A.take<float>(n);
+  w->w_ceil = A.take<float>(n);
+  w->cum = A.take<int>(n);
+  w->zbuf = A.take<float>((size_t)B * c.inter_channels * max_frames);
+  size_t s1 = wetts_text_encoder_workspace_bytes(h, B, Tx);
+  size_t s2 = wetts_duration_workspace_bytes(h, B, Tx);
+  size_t s3 = wetts_flow_workspace_bytes(h, B, max_frames);
+  size_t s4 = wetts_generator_workspace_bytes(h, B, max_frames);
+  size_t mx = s1 > s2 ? s1 : s2;
+  mx = mx > s3 ? mx : s3;
+  mx = mx > s4 ? mx : s4;
+  w->scratch = A.take<char>(mx);
+  w->scratch_bytes = mx;
+  return A.off;
+}
+size_t wetts_vits_infer_workspace_bytes(wetts_vits_t h, int B, int Tx, int max_frames) {
+  if (!h) return 0;
+  Arena A(nullptr, 0);
+  InferWs w;
+  return infer_layout(h, B, Tx, max_frames < 1 ? 1 : max_frames, A, &w) + 256;
+}
+
+int wetts_vits_infer_durations(wetts_vits_t h, const int64_t* ids, const int64_t* x_lengths, const int64_t* sid,
+                               const float* scales3, const float* noise_w, const float* durations, int B, int Tx,
+                               int64_t* y_lengths, float* logw_out, float* w_ceil_out, int* max_frames_host,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  CHECK_READY(h);
+  if (!scales3 || !y_lengths || !max_frames_host) return fail("null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena A(workspace, workspace_bytes);
+  InferWs w;
+  infer_layout(h, B, Tx, 1, A, &w);  // stage 1 needs only the persistent part + Tx-sized scratch
+  if (!workspace) return fail("null workspace");
+  // the persistent prefix does not depend on max_frames; scratch starts after zbuf, so recompute it for this size
+  if (!A.ok()) return fail("infer workspace too small: need at least %zu bytes", A.off);
+  const wetts_vits_config& c = h->cfg;
+  const float* g = nullptr;
+  if (c.n_speakers > 0) {
+    if (!sid) return fail("sid is required for a multi-speaker model");
+    if (wetts_speaker_embedding(h, sid, B, w.g, stream)) return 1;
+    g = w.g;
+  }
+  // Stage-1 scratch: use the tail of the caller's workspace (everything after the persistent prefix)
+  char* tail = (char*)w.zbuf;
+  const size_t tail_bytes = workspace_bytes - (size_t)(tail - (char*)workspace);
+  if (wetts_text_encoder_forward(h, ids, x_lengths, B, Tx, w.hbuf, w.m, w.logs, tail, tail_bytes, stream)) return 1;
+  if (wetts_duration_forward(h, w.hbuf, x_lengths, g, noise_w, scales3[2], B, Tx, w.logw, tail, tail_bytes, stream)) return 1;
+  if (wetts_length_regulate(h, w.logw, x_lengths, durations, scales3[1], B, Tx, w.w_ceil, w.cum, y_lengths, stream)) return 1;
+  launch_max_i64((const long long*)y_lengths, B, h->dev_scalar, s);
+  CUDA_OK(cudaMemcpyAsync(h->host_pinned, h->dev_scalar, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  if (logw_out) CUDA_OK(cudaMemcpyAsync(logw_out, w.logw, sizeof(float) * B * Tx, cudaMemcpyDeviceToDevice, s));
+  if (w_ceil_out) CUDA_OK(cudaMemcpyAsync(w_ceil_out, w.w_ceil, sizeof(float) * B * Tx, cudaMemcpyDeviceToDevice, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  *max_frames_host = (int)h->host_pinned[0];
+  return 0;
+}
+
+int wetts_vits_infer_synthesize(wetts_vits_t h, const int64_t* x_lengths, const int64_t* y_lengths, const float* scales3,
+                                const float* noise_z, int64_t noise_bs, int64_t noise_rs, int B, int Tx, int Ty,
+                                float* audio, float* attn, float* y_mask, float* z, float* z_p, float* m_p, float* logs_p,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  CHECK_READY(h);
+  if (!audio || !scales3 || !noise_z) return fail("null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  Arena A(workspace, workspace_bytes);
+  InferWs w;
+  infer_layout(h, B, Tx, Ty, A, &w);
+  if (!workspace || !A.ok()) return fail("infer workspace too small: need %zu bytes for Ty=%d", A.off, Ty);
+  const wetts_vits_config& c = h->cfg;
+  const float* g = c.n_speakers > 0 ? w.g : nullptr;
+  float* zb = z ? z : w.zbuf;
+  float* zp_dst = z_p ? z_p : zb;
+  if (wetts_expand_prior(h, w.m, w.logs, w.cum, x_lengths, y_lengths, noise_z, noise_bs, noise_rs, scales3[0], B, Tx, Ty,
+                         m_p, logs_p, zp_dst, attn, y_mask, stream))
+    return 1;
+  if (zp_dst != zb)
+    CUDA_OK(cudaMemcpyAsync(zb, zp_dst, sizeof(float) * (size_t)B * c.inter_channels * Ty, cudaMemcpyDeviceToDevice, s));
+  if (wetts_flow_reverse(h, zb, y_lengths, g, B, Ty, w.scratch, w.scratch_bytes, stream)) return 1;
+  if (wetts_generator_forward(h, zb, y_lengths, g, B, Ty, audio, w.scratch, w.scratch_bytes, stream)) return 1;
+  return 0;
+}
+
+// ------------------------------------------------------------------ L2 decoder contract
+size_t wetts_vits_decoder_workspace_bytes(wetts_vits_t h, int B, int L) {
+  if (!h) return 0;
+  return wetts_generator_workspace_bytes(h, B, L) + sizeof(float) * ((size_t)B * h->cfg.inter_channels * L +
+                                                                     (size_t)B * (h->cfg.gin_channels + 1)) + 1024;
+}
+int wetts_vits_forward_decoder(wetts_vits_t h, const float* z_blc, const int64_t* sid, int B, int L, float* audio,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  CHECK_READY(h);
+  if (!workspace || workspace_bytes < wetts_vits_decoder_workspace_bytes(h, B, L))
+    return fail("decoder workspace too small: need %zu bytes", wetts_vits_decoder_workspace_bytes(h, B, L));
+  Arena A(workspace, workspace_bytes);
+  float* zt = A.take<float>((size_t)B * h->cfg.inter_channels * L);
+  float* g = A.take<float>((size_t)B * (h->cfg.gin_channels + 1));
+  A.off = (A.off + 255) & ~(size_t)255;
+  launch_transpose_blc(z_blc, zt, B, L, h->cfg.inter_channels, (cudaStream_t)stream);
+  const float* gp = nullptr;
+  if (h->cfg.n_speakers > 0) {
+    if (!sid) return fail("sid is required for a multi-speaker model");
+    if (wetts_speaker_embedding(h, sid, B, g, stream)) return 1;
+    gp = g;
+  }
+  return wetts_generator_forward(h, zt, nullptr, gp, B, L, audio, (char*)workspace + A.off, workspace_bytes - A.off, stream);
+}
+
+}  // extern "C"

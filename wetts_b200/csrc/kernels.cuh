@@ -1,0 +1,133 @@
+// Internal kernel interface of libwetts_b200 (sm_100a).  Not part of the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wetts {
+
+// ---------------------------------------------------------------- conv1d (fp32 SIMT)
+enum EpiMode : int {
+  EPI_PLAIN = 0,     // out = act(v + cond) [* mask]
+  EPI_RESID = 1,     // out = v + resid                         (ResBlock inner add)
+  EPI_MRF = 2,       // val = v + resid; acc_mode 0: out=val, 1: out+=val, 2: out=(out+val)/div
+  EPI_GATE = 3,      // paired channels -> tanh(a+ga)*sigmoid(b+gb)   (modules.py:76-77)
+  EPI_RES_SKIP = 4,  // co<H: x=(x+v)*mask ; co>=H: skip(+)=v         (modules.py:81-86)
+  EPI_COUPLING = 5,  // z1 = (z1 - v*mask)*mask                       (flows.py:510)
+};
+
+struct ConvEpilogue {
+  int mode = EPI_PLAIN;
+  float* out = nullptr;      // [B][*][T], batch stride out_bs, channel stride T
+  long long out_bs = 0;
+  const float* resid = nullptr;  // same geometry as out
+  const float* cond = nullptr;   // per (b, co) additive term, cond[b*cond_bs + cond_off + co]
+  int cond_bs = 0;
+  int cond_off = 0;
+  int act = 0;               // 0 none, 1 relu
+  int out_mask = 0;          // multiply result by (t < lengths[b])
+  int acc_mode = 0;          // EPI_MRF
+  float div = 1.f;           // EPI_MRF final divisor
+  int H = 0;                 // EPI_GATE / EPI_RES_SKIP hidden size
+  float* x = nullptr;        // EPI_RES_SKIP residual stream (in place), batch stride out_bs
+  float* skip = nullptr;     // EPI_RES_SKIP skip accumulator, batch stride out_bs
+  int skip_init = 0;         // 1: skip = v (first layer), 0: skip += v
+  int last = 0;              // last WN layer: all Cout channels go to skip
+  int z_c0 = 0;              // EPI_COUPLING: target channel = z_c0 + co*z_cstep in `out`
+  int z_cstep = 1;
+};
+
+struct ConvArgs {
+  const float* in = nullptr;  // [B][Cin][T] view: element (b,ci,t) at in + b*in_bs + ci*in_cs + t
+  long long in_bs = 0;
+  int in_cs = 0;
+  const float* w = nullptr;   // packed [Cin][K][CoutPad]
+  const float* bias = nullptr;  // packed [CoutPad] or nullptr
+  int B = 0, Cin = 0, Cout = 0, CoutPad = 0, T = 0, K = 1, dil = 1, pad_left = 0;
+  int pre_act = 0;            // 1: leaky_relu(pre_slope) applied to the input
+  float pre_slope = 0.1f;
+  const long long* lengths = nullptr;  // int64[B] or nullptr
+  int in_mask = 0;            // multiply the input by (t < lengths[b])
+  ConvEpilogue ep;
+};
+void launch_conv1d(const ConvArgs& a, cudaStream_t s);
+
+struct ConvTArgs {
+  const float* in = nullptr;  // [B][Cin][T]
+  const float* w = nullptr;   // packed [Cin][ntaps][CoutPad][u]
+  const float* bias = nullptr;
+  float* out = nullptr;       // [B][Cout][T*u]
+  int B = 0, Cin = 0, Cout = 0, CoutPad = 0, T = 0, u = 1, ntaps = 2, pad = 0;
+  float pre_slope = 0.1f;     // leaky_relu on the input (decoders.py:69)
+};
+void launch_conv_transpose1d(const ConvTArgs& a, cudaStream_t s);
+
+// conv_post: lrelu(slope) -> Conv1d(C->1, k, no bias) -> tanh   (decoders.py:78-80)
+void launch_conv_post_tanh(const float* in, const float* w /*[C][K]*/, float* out, int B, int C, int T, int K,
+                           float slope, cudaStream_t s);
+
+// ---------------------------------------------------------------- weight preparation
+void launch_weight_norm_fold(const float* v, const float* g, float* out, int rows, int cols, cudaStream_t s);
+// dst[ci][k][p] = src[co_map[p]][ci_map[ci]][k]   (co_map[p] < 0 -> 0)
+void launch_pack_conv(const float* src, float* dst, const int* co_map, const int* ci_map, int Cin, int K, int CoutPad,
+                      int src_cin, cudaStream_t s);
+// dst[ci][tap][co][r] = src[ci][co][r + tap*u]  (src [Cin][Cout][k]); co >= Cout -> 0
+void launch_pack_convT(const float* src, float* dst, int Cin, int Cout, int CoutPad, int k, int u, cudaStream_t s);
+void launch_gather_vec(const float* src, float* dst, const int* map, int n, cudaStream_t s);
+
+// ---------------------------------------------------------------- elementwise / norm
+void launch_embed(const long long* ids, const long long* lengths, const float* table, float* out, int B, int Tx, int H,
+                  int n_vocab, float scale, cudaStream_t s);
+void launch_speaker_embed(const long long* sid, const float* table, float* g, int B, int gin, int n_speakers,
+                          cudaStream_t s);
+
+struct LnArgs {
+  const float* a = nullptr;      // [B][C][T]
+  const float* b = nullptr;      // optional addend (same shape)
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  const float* res = nullptr;    // optional: out = res + y
+  float* out = nullptr;
+  const long long* lengths = nullptr;
+  // optional depthwise front-end: a' = dwbias[c] + sum_k dww[c][k] * a[c][t+(k-1)*dil] * mask(t+(k-1)*dil)
+  const float* dww = nullptr;    // [C][3]
+  const float* dwb = nullptr;
+  int dil = 1;
+  int act = 0;                   // 0 none, 1 gelu(erf)
+  int out_mask = 0;
+  int B = 0, C = 0, T = 0;
+  float eps = 1e-5f;
+};
+void launch_layernorm(const LnArgs& a, cudaStream_t s);
+
+// relative-position multi-head attention core (attentions.py:232-282)
+// qkv [B][3C][T] (q rows 0..C-1, k rows C..2C-1, v rows 2C..3C-1), out [B][C][T]
+void launch_rel_attention(const float* qkv, const float* emb_k, const float* emb_v, const long long* lengths, float* out,
+                          int B, int C, int T, int n_heads, int window, cudaStream_t s);
+
+// ---------------------------------------------------------------- stochastic duration predictor
+// h[b][c][t] = w[c]*z[b][src_ch][t] + bias[c] + cond[b][c][t]    (ConvFlow.pre + DDSConv `x + g`)
+void launch_convflow_pre(const float* z, int src_ch, const float* w, const float* bias, const float* cond, float* out,
+                         int B, int C, int T, cudaStream_t s);
+// zout[b][0][t] = zin[b][1][t]*m ; zout[b][1][t] = RQS^-1(zin[b][0][t]; u[b][0:29][t])*m   (Flip + ConvFlow reverse)
+void launch_spline_flip(const float* zin, const float* u /*[B][32pad?]*/, int u_cs_rows, float* zout,
+                        const long long* lengths, int B, int T, float inv_sqrt_h, cudaStream_t s);
+void launch_scale(const float* in, float* out, float scale, long long n, cudaStream_t s);
+// logw[b][t] = (z[b][1][t] - m0) * exp(-logs0) * mask   (final Flip + ElementwiseAffine reverse, channel 0)
+void launch_sdp_final(const float* z, const float* m, const float* logs, const long long* lengths, float* logw, int B,
+                      int T, cudaStream_t s);
+
+// ---------------------------------------------------------------- length regulation
+void launch_length_regulate(const float* logw, const long long* x_lengths, const float* durations, float length_scale,
+                            int B, int Tx, float* w_ceil, int* cum, long long* y_lengths, cudaStream_t s);
+void launch_expand_prior(const float* m, const float* logs, const int* cum, const long long* x_lengths,
+                         const long long* y_lengths, const float* noise, long long noise_bs, long long noise_rs,
+                         float noise_scale, int B, int C, int Tx, int Ty, float* m_p, float* logs_p, float* z_p,
+                         float* attn, float* y_mask, cudaStream_t s);
+void launch_max_i64(const long long* v, int n, long long* out, cudaStream_t s);
+// [B][L][C] -> [B][C][L]
+void launch_transpose_blc(const float* in, float* out, int B, int L, int C, cudaStream_t s);
+
+unsigned long long kernel_launch_counter();
+void count_launch();
+
+}  // namespace wetts
