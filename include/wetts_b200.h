@@ -70,6 +70,11 @@ typedef struct wetts_vits_config {
 const char* wetts_last_error(void);
 const char* wetts_version(void);
 
+/* Process-wide options.  "tensor_cores": 1 (default) routes eligible convolutions through the
+ * tcgen05 3xTF32 implicit-GEMM kernel (fp32-accurate), 0 forces the fp32 SIMT kernels. */
+int wetts_set_option(const char* name, int value);
+int wetts_get_option(const char* name, int* value);
+
 /* ---- lifetime ---------------------------------------------------------- */
 int wetts_vits_create(const wetts_vits_config* cfg, int device, wetts_vits_t* out);
 /* Register one checkpoint tensor under its reference state-dict key

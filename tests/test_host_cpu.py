@@ -1,0 +1,79 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, host logic
+(config mirror, synthetic checkpoints, loud failure without a GPU)."""
+import os
+import re
+
+import pytest
+import torch
+
+import wetts_b200
+from wetts_b200 import _lib, synth
+from wetts_b200.hparams import HParams, builtin_config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from wetts_b200 import build
+    build.build()
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "wetts_b200.h")).read()
+    declared = set(re.findall(r"\b(wetts_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.wetts_version()
+
+
+def test_hparams_mapping_protocol():
+    hps = builtin_config("multilingual_v3")
+    assert hps.data.sampling_rate == 16000 and hps["model"]["use_sdp"] is False
+    assert "model" in hps and len(hps) == 3
+    kw = dict(**hps.model)
+    assert kw["upsample_rates"] == [8, 8, 4]
+    h2 = HParams(a={"b": 1})
+    assert h2.a.b == 1 and list(h2.keys()) == ["a"]
+
+
+def test_synthetic_checkpoint_is_deterministic_and_nontrivial():
+    hps = builtin_config("baker_v1")
+    a = synth.make_state_dict(hps.model, 50, 1, seed=1234)
+    b = synth.make_state_dict(hps.model, 50, 1, seed=1234)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+    assert synth.fingerprint(a) == synth.fingerprint(b)
+    # tensors the reference zero-initialises must be non-zero (SURVEY §0 finding 5)
+    assert a["flow.flows.0.post.weight"].abs().max() > 0
+    assert a["dp.flows.1.proj.weight"].abs().max() > 0
+    v, g = a["dec.ups.0.weight_v"], a["dec.ups.0.weight_g"]
+    assert g.shape == (v.shape[0], 1, 1)          # ConvTranspose1d: per INPUT channel
+    assert not torch.allclose(g.flatten(), v.reshape(v.shape[0], -1).norm(dim=1))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_gpu():
+    hps = builtin_config("multilingual_v3")
+    net = wetts_b200.SynthesizerTrn(10, 513, 32, n_speakers=1, **hps.model)
+    with pytest.raises(wetts_b200.WettsError):
+        net.to("cuda")
+    with pytest.raises(wetts_b200.WettsError):
+        net.infer(torch.zeros(1, 4, dtype=torch.long), torch.tensor([4]), torch.tensor([0]))
+
+
+def test_unsupported_variants_raise():
+    hps = builtin_config("multilingual_v3")
+    with pytest.raises(NotImplementedError):
+        wetts_b200.SynthesizerTrn(10, 513, 32, n_speakers=1, vocoder_type="vocos", **hps.model)
+    with pytest.raises(NotImplementedError):
+        wetts_b200.SynthesizerTrn(10, 513, 32, n_speakers=1, use_transformer_flows=True, **hps.model)
+
+
+def test_reference_loads_synthetic_checkpoint():
+    """Where the reference tree exists (authoring container) the synthetic state dict must load
+    into the reference's own module with nothing unexpected and only enc_q.* missing."""
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference tree not present")
+    for cfg in ("multilingual_v3", "baker_v1"):
+        hps = builtin_config(cfg)
+        sd = synth.make_state_dict(hps.model, 40, 2, seed=3)
+        ref_harness.build_reference_model(hps, 40, 2, sd)

@@ -17,7 +17,12 @@ def rep(tag, a, b):
 
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
-    for name in CASES:
+    from wetts_b200 import _lib
+    tc = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    _lib.check(_lib.load().wetts_set_option(b"tensor_cores", tc))
+    print("tensor_cores =", tc, flush=True)
+    cases = sys.argv[2:] if len(sys.argv) > 2 else CASES
+    for name in cases:
         print("case", name, flush=True)
         try:
             hps, sd, g, t = load_case(name)

@@ -31,6 +31,8 @@ _P, _I, _F, _SZ, _I64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 PROTOTYPES = {
     "wetts_last_error": (C.c_char_p, []),
     "wetts_version": (C.c_char_p, []),
+    "wetts_set_option": (_I, [C.c_char_p, _I]),
+    "wetts_get_option": (_I, [C.c_char_p, C.POINTER(_I)]),
     "wetts_vits_create": (_I, [C.POINTER(VitsConfig), _I, C.POINTER(_P)]),
     "wetts_vits_set_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(_I64), _I]),
     "wetts_vits_finalize": (_I, [_P]),

@@ -11,6 +11,7 @@
 #include <cstdio>
 
 #include "kernels.cuh"
+#include "epilogue.cuh"
 
 namespace wetts {
 
@@ -23,8 +24,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kCiChunk = 16;
 constexpr int kTM = 8;
-
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
 
 template <int TN, int WARPS_CO>
 __global__ void __launch_bounds__(kThreads, 2) conv1d_kernel(const ConvArgs a) {
@@ -111,28 +110,19 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_kernel(const ConvArgs a) {
     }
   }
 
-  // ---- epilogue
-  const ConvEpilogue& e = a.ep;
+  // ---- epilogue (shared with the tensor-core kernel: epilogue.cuh)
   const int co_base = co_blk + co0;
-  if (e.mode == EPI_GATE) {
-    const int H = e.H;
+  if (a.ep.mode == EPI_GATE) {
 #pragma unroll
     for (int m = 0; m < kTM; m += 2) {
       const int co = co_base + m;
       if (co >= a.Cout) continue;
-      const int jch = co >> 1;
-      float ba = 0.f, bb = 0.f;
-      if (a.bias) { ba = a.bias[co]; bb = a.bias[co + 1]; }
-      if (e.cond) {
-        const float* g = e.cond + (long long)b * e.cond_bs + e.cond_off;
-        ba += g[jch];
-        bb += g[H + jch];
-      }
-      float* o = e.out + (long long)b * e.out_bs + (long long)jch * T;
+      float ba, bb;
+      gate_terms(a, b, co, ba, bb);
 #pragma unroll
       for (int j = 0; j < TN; ++j) {
         const int t = t0 + tl + 32 * j;
-        if (t < T) o[t] = tanhf(acc[m][j] + ba) * sigmoidf_acc(acc[m + 1][j] + bb);
+        if (t < T) gate_store(a, b, co, t, acc[m][j] + ba, acc[m + 1][j] + bb);
       }
     }
     return;
@@ -141,50 +131,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_kernel(const ConvArgs a) {
   for (int m = 0; m < kTM; ++m) {
     const int co = co_base + m;
     if (co >= a.Cout) continue;
-    float bv = a.bias ? a.bias[co] : 0.f;
-    if (e.mode == EPI_PLAIN && e.cond) bv += e.cond[(long long)b * e.cond_bs + e.cond_off + co];
+    const float bv = channel_term(a, b, co);
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int t = t0 + tl + 32 * j;
-      if (t >= T) continue;
-      float v = acc[m][j] + bv;
-      const float msk = (t < len) ? 1.f : 0.f;
-      const long long off = (long long)b * e.out_bs + (long long)co * T + t;
-      switch (e.mode) {
-        case EPI_PLAIN:
-          if (e.act == 1) v = fmaxf(v, 0.f);
-          if (e.out_mask) v *= msk;
-          e.out[off] = v;
-          break;
-        case EPI_RESID:
-          e.out[off] = v + e.resid[off];
-          break;
-        case EPI_MRF: {
-          v += e.resid[off];
-          if (e.acc_mode == 0) e.out[off] = v;
-          else if (e.acc_mode == 1) e.out[off] = e.out[off] + v;
-          else e.out[off] = (e.out[off] + v) / e.div;
-          break;
-        }
-        case EPI_RES_SKIP: {
-          if (!e.last && co < e.H) {
-            e.x[off] = (e.x[off] + v) * msk;
-          } else {
-            const int c2 = e.last ? co : co - e.H;
-            const long long o2 = (long long)b * e.out_bs + (long long)c2 * T + t;
-            e.skip[o2] = e.skip_init ? v : e.skip[o2] + v;
-          }
-          break;
-        }
-        case EPI_COUPLING: {
-          const int zc = e.z_c0 + co * e.z_cstep;
-          float* p = e.out + (long long)b * e.out_bs + (long long)zc * T + t;
-          *p = (*p - v * msk) * msk;
-          break;
-        }
-        default:
-          break;
-      }
+      if (t < T) epilogue_store(a, b, co, t, acc[m][j] + bv, (t < len) ? 1.f : 0.f);
     }
   }
 }
@@ -363,6 +314,11 @@ __global__ void __launch_bounds__(kThreads) conv_post_kernel(const float* __rest
 }  // namespace
 
 void launch_conv1d(const ConvArgs& a, cudaStream_t s) {
+  if (a.wtc && a.T >= 64 && a.dil == a.tc.dil && tensor_cores_enabled()) launch_conv1d_tc(a, s);
+  else launch_conv1d_simt(a, s);
+}
+
+void launch_conv1d_simt(const ConvArgs& a, cudaStream_t s) {
   const bool wide = (a.CoutPad % 64) == 0;
   const int T = a.T;
   if (wide) {

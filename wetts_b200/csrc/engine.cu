@@ -46,8 +46,10 @@ struct Raw {
 };
 
 struct Conv {
-  float* w = nullptr;
+  float* w = nullptr;    // SIMT layout [Cin][K][CoutPad]
   float* b = nullptr;
+  float* wtc = nullptr;  // tcgen05 layout (tc_conv_kernel.cu), hi/lo tf32 split
+  TcPlan tc;
   int Cin = 0, Cout = 0, CoutPad = 0, K = 1;
 };
 struct ConvT {
@@ -184,7 +186,7 @@ struct wetts_vits_s {
   // Conv1d weight [Cout][Cin][K] -> packed [Cin'][K][CoutPad]; co_map: packed out channel -> source
   // out channel (empty: identity); ci_map: packed in channel -> source in channel (empty: identity)
   int pack_conv_from(const Raw& w, const float* bias_src, std::vector<int> co_map, const std::vector<int>& ci_map,
-                     Conv* c) {
+                     Conv* c, int tc_dil = 1) {
     if (w.dims.size() != 3) return fail("conv weight must be 3-D");
     const int src_cout = (int)w.dims[0], src_cin = (int)w.dims[1], K = (int)w.dims[2];
     if (co_map.empty()) {
@@ -206,10 +208,15 @@ struct wetts_vits_s {
       if (dalloc(&c->b, (size_t)c->CoutPad)) return 1;
       launch_gather_vec(bias_src, c->b, d_co, c->CoutPad, 0);
     }
+    c->wtc = nullptr;
+    if (tc_dil > 0 && tc_conv_plan(c->Cin, c->Cout, K, tc_dil, &c->tc)) {
+      if (dalloc(&c->wtc, c->tc.packed_floats)) return 1;
+      launch_pack_conv_tc(w.d, c->wtc, d_co, d_ci, c->Cout, c->Cin, K, src_cin, c->tc, 0);
+    }
     return 0;
   }
   int make_conv(const std::string& prefix, Conv* c, bool bias = true, std::vector<int> co_map = {},
-                const std::vector<int>& ci_map = {}) {
+                const std::vector<int>& ci_map = {}, int tc_dil = 1) {
     Raw w;
     if (folded_weight(prefix, &w)) return 1;
     const float* bsrc = nullptr;
@@ -218,7 +225,7 @@ struct wetts_vits_s {
       if (need(prefix + ".bias", &b)) return 1;
       bsrc = b->d;
     }
-    return pack_conv_from(w, bsrc, co_map, ci_map, c);
+    return pack_conv_from(w, bsrc, co_map, ci_map, c, tc_dil);
   }
   int make_ln(const std::string& prefix, Ln* l) {
     const Raw *g, *b;
@@ -250,6 +257,8 @@ namespace wetts {
 
 static ConvArgs conv_args(const Conv& c, const float* in, long long in_bs, int in_cs, int B, int T, int dil = 1) {
   ConvArgs a;
+  a.wtc = c.wtc;
+  a.tc = c.tc;
   a.in = in;
   a.in_bs = in_bs;
   a.in_cs = in_cs;
@@ -371,6 +380,23 @@ void wetts_vits_destroy(wetts_vits_t h) {
 }
 
 int wetts_vits_upsample_factor(wetts_vits_t h) { return h ? h->U : 0; }
+
+int wetts_set_option(const char* name, int value) {
+  if (!name) return fail("null option name");
+  if (!strcmp(name, "tensor_cores")) {
+    set_tensor_cores_enabled(value != 0);
+    return 0;
+  }
+  return fail("unknown option '%s'", name);
+}
+int wetts_get_option(const char* name, int* value) {
+  if (!name || !value) return fail("null argument");
+  if (!strcmp(name, "tensor_cores")) {
+    *value = tensor_cores_enabled() ? 1 : 0;
+    return 0;
+  }
+  return fail("unknown option '%s'", name);
+}
 uint64_t wetts_vits_launch_count(wetts_vits_t h) { return h ? kernel_launch_counter() - h->launches_at_create : 0; }
 
 int wetts_vits_set_tensor(wetts_vits_t h, const char* name, const void* data, const int64_t* dims, int ndim) {
@@ -535,12 +561,13 @@ int wetts_vits_finalize(wetts_vits_t h) {
           rb.dil.push_back(c.resblock_dilations[j][n]);
           Conv a, bq;
           if (c.resblock_type == 1) {
-            if (h->make_conv(rp + ".convs1." + std::to_string(n), &a) || h->make_conv(rp + ".convs2." + std::to_string(n), &bq))
+            if (h->make_conv(rp + ".convs1." + std::to_string(n), &a, true, {}, {}, rb.dil.back()) ||
+                h->make_conv(rp + ".convs2." + std::to_string(n), &bq))
               return 1;
             rb.c1.push_back(a);
             rb.c2.push_back(bq);
           } else {
-            if (h->make_conv(rp + ".convs." + std::to_string(n), &a)) return 1;
+            if (h->make_conv(rp + ".convs." + std::to_string(n), &a, true, {}, {}, rb.dil.back())) return 1;
             rb.c1.push_back(a);
           }
           if (a.K != rb.k || a.Cin != ch) return fail("%s: shape does not match the config", rp.c_str());

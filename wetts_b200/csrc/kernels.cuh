@@ -36,7 +36,15 @@ struct ConvEpilogue {
   int z_cstep = 1;
 };
 
+// tiling of the tcgen05 implicit-GEMM path (tc_conv_kernel.cu), fixed per conv at load time
+struct TcPlan {
+  int N = 0, n_tiles = 0, KC = 0, n_chunks = 0, MB = 0, G = 0, n_bbuf = 0, R_pad = 0, dil = 1;
+  size_t packed_floats = 0;
+};
+
 struct ConvArgs {
+  const float* wtc = nullptr;  // tensor-core packed weights (nullptr: SIMT path only)
+  TcPlan tc;
   const float* in = nullptr;  // [B][Cin][T] view: element (b,ci,t) at in + b*in_bs + ci*in_cs + t
   long long in_bs = 0;
   int in_cs = 0;
@@ -50,6 +58,20 @@ struct ConvArgs {
   ConvEpilogue ep;
 };
 void launch_conv1d(const ConvArgs& a, cudaStream_t s);
+void launch_conv1d_simt(const ConvArgs& a, cudaStream_t s);
+
+struct TcConvArgs {
+  ConvArgs c;
+  const float* wtc;
+  int N, n_tiles, KC, n_chunks, MB, G, n_bbuf, R_pad;
+};
+bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan);
+size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_bbuf);
+void launch_pack_conv_tc(const float* src, float* dst, const int* co_map, const int* ci_map, int Cout, int Cin, int K,
+                         int src_cin, const TcPlan& pl, cudaStream_t s);
+void launch_conv1d_tc(const ConvArgs& a, cudaStream_t s);
+void set_tensor_cores_enabled(bool on);
+bool tensor_cores_enabled();
 
 struct ConvTArgs {
   const float* in = nullptr;  // [B][Cin][T]

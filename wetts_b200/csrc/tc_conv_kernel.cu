@@ -1,0 +1,409 @@
+// tcgen05 (5th-gen tensor core) implicit-GEMM Conv1d for sm_100a, fp32-accurate via 3xTF32.
+//
+//   D[time, co] = sum_{tap, ci} A[time + tap*dil, ci] * W[co, ci, tap]
+//
+// * M = 128 time rows per MMA, N = C_out tile (<= 256), K = 8 input channels per tcgen05.mma
+//   (kind::tf32).  Accumulators live in TMEM (512 columns = up to 8 resident 128xN tiles), read
+//   back with tcgen05.ld for the fused epilogue (epilogue.cuh: bias / residual / MRF mean /
+//   WaveNet gate / res-skip / coupling update).
+// * Operands are staged in shared memory in the no-swizzle K-major canonical layout
+//   (8 rows x 16 B core matrices): element (row r, channel c) at (c/4)*LBO + r*16 + (c%4)*4.
+//   With SBO = 128 B all rows of a 4-channel group are contiguous at a 16 B pitch, so a conv tap
+//   is just a +tap*dil*16 B shift of the descriptor start address: no im2col, one staged tile
+//   serves every tap and dilation.
+// * fp32 accuracy: x = hi + lo with hi = tf32(x), lo = tf32(x - hi); three MMAs per product
+//   (hi*hi, hi*lo, lo*hi) accumulate in fp32 (error ~2^-21 relative, far inside the stated
+//   tolerance; plain TF32 would not be).  Weights are split once at load time; activations are
+//   split while they are staged (together with leaky-relu, masks and zero padding).
+// * Weights arrive by cp.async.bulk (TMA 1-D bulk copy) + mbarrier; tcgen05.commit signals
+//   buffer reuse and accumulator completion; one persistent CTA per SM loops over work items
+//   and keeps the weight tile resident when it can.
+#include <cstdint>
+
+#include "epilogue.cuh"
+#include "kernels.cuh"
+
+namespace wetts {
+namespace {
+
+constexpr int kTcThreads = 256;
+constexpr uint32_t kTmemCols = 512;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// shared-memory matrix descriptor: K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvArgs p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const ConvArgs& a = p.c;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K = a.K, dil = a.dil, T = a.T;
+  const int N = p.N, KC = p.KC, MB = p.MB, MT = 128 * p.MB;
+  const int R = MT + (K - 1) * dil;
+  const int Rp = p.R_pad;
+  const uint32_t a_half = (uint32_t)KC * Rp * 4;       // bytes of one hi or lo activation tile
+  const uint32_t a_bytes = 2 * a_half;
+  const uint32_t b_half = (uint32_t)K * KC * N * 4;    // bytes of one hi or lo weight tile
+  const uint32_t b_bytes = 2 * b_half;
+  const int nb = p.n_bbuf;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
+  uint8_t* A0 = smem + 128;
+  uint8_t* B0 = A0 + 2 * a_bytes;
+  const uint32_t bar_a_free = smem_u32(&bars[0]);   // [2]
+  const uint32_t bar_b_full = smem_u32(&bars[2]);   // [2]
+  const uint32_t bar_b_free = smem_u32(&bars[4]);   // [2]
+  const uint32_t bar_acc = smem_u32(&bars[6]);
+  const uint32_t A_addr = smem_u32(A0), B_addr = smem_u32(B0);
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 7; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  const int G = p.G;
+  const int group_rows = G * MT;
+  const int n_groups = (T + group_rows - 1) / group_rows;
+  const int items_per_nt = a.B * n_groups;
+  const int n_items = items_per_nt * p.n_tiles;
+
+  uint32_t a_uses[2] = {0, 0};       // completed stagings per A buffer
+  uint32_t b_loads[2] = {0, 0};      // loads issued per B buffer
+  uint32_t acc_count = 0;
+  int b_resident_nt = -1;            // weight tile resident in B[0] (single-chunk layers)
+  uint32_t a_count = 0, b_count = 0;
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int nt = item / items_per_nt;
+    const int rem = item - nt * items_per_nt;
+    const int b = rem / n_groups;
+    const int t_group0 = (rem - b * n_groups) * group_rows;
+    const int tiles = min(G, (T - t_group0 + MT - 1) / MT);
+    const long long len = a.lengths ? a.lengths[b] : (long long)T;
+    const int t_hi = a.in_mask ? (int)(len < T ? len : T) : T;
+    const float* in_b = a.in + (long long)b * a.in_bs;
+
+    for (int c = 0; c < p.n_chunks; ++c) {
+      // ---------------- weights for (nt, c)
+      int bb = 0;
+      bool load_b = true;
+      if (p.n_chunks == 1) {
+        load_b = (b_resident_nt != nt);
+        b_resident_nt = nt;
+      } else {
+        bb = (nb == 2) ? (int)(b_count & 1) : 0;
+      }
+      if (load_b) {
+        // multi-chunk layers: the MMAs that last read this buffer committed to b_free; single-chunk
+        // layers reload only across work items, whose MMAs the accumulator barrier already covered
+        if (p.n_chunks > 1 && b_loads[bb] > 0) mbar_wait(bar_b_free + 8 * bb, (b_loads[bb] - 1) & 1);
+        if (tid == 0) {
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + c) * b_bytes;
+          mbar_expect_tx(bar_b_full + 8 * bb, b_bytes);
+          uint32_t off = 0;
+          while (off < b_bytes) {
+            const uint32_t n = min(b_bytes - off, 32768u);
+            bulk_g2s(B_addr + bb * b_bytes + off, src + off, n, bar_b_full + 8 * bb);
+            off += n;
+          }
+        }
+      }
+      const int c0 = c * KC;
+      for (int g = 0; g < tiles; ++g) {
+        const int ab = (int)(a_count & 1);
+        if (a_uses[ab] > 0) mbar_wait(bar_a_free + 8 * ab, (a_uses[ab] - 1) & 1);
+        // ---------------- stage activations: rows [t_tile0 - pad, +R), channels [c0, c0+KC)
+        {
+          uint8_t* Ah = A0 + ab * a_bytes;
+          const int t_in0 = t_group0 + g * MT - a.pad_left;
+          for (int cg = 0; cg < KC / 4; ++cg) {
+            const int ci0 = c0 + cg * 4;
+            const float* src = in_b + (long long)ci0 * a.in_cs;
+            float4* dst_hi = reinterpret_cast<float4*>(Ah + (size_t)cg * Rp * 16);
+            float4* dst_lo = reinterpret_cast<float4*>(Ah + a_half + (size_t)cg * Rp * 16);
+            for (int r = tid; r < Rp; r += kTcThreads) {
+              const int t = t_in0 + r;
+              float v[4] = {0.f, 0.f, 0.f, 0.f};
+              if (r < R && t >= 0 && t < t_hi) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (ci0 + e < a.Cin) {
+                    float x = __ldg(src + (long long)e * a.in_cs + t);
+                    if (a.pre_act) x = x > 0.f ? x : x * a.pre_slope;
+                    v[e] = x;
+                  }
+                }
+              }
+              float4 hi, lo;
+              hi.x = tf32_rna(v[0]); lo.x = tf32_rna(v[0] - hi.x);
+              hi.y = tf32_rna(v[1]); lo.y = tf32_rna(v[1] - hi.y);
+              hi.z = tf32_rna(v[2]); lo.z = tf32_rna(v[2] - hi.z);
+              hi.w = tf32_rna(v[3]); lo.w = tf32_rna(v[3] - hi.w);
+              dst_hi[r] = hi;
+              dst_lo[r] = lo;
+            }
+          }
+        }
+        fence_async_smem();
+        __syncthreads();
+        // ---------------- issue the MMAs of (tile g, chunk c)
+        if (tid == 0) {
+          if (load_b && g == 0) mbar_wait(bar_b_full + 8 * bb, b_loads[bb] & 1);
+          tc_fence_after();
+          const uint64_t adesc0 = make_desc(A_addr + ab * a_bytes, (uint32_t)Rp * 16, 128);
+          const uint64_t bdesc0 = make_desc(B_addr + bb * b_bytes, (uint32_t)N * 16, 128);
+          for (int mb = 0; mb < MB; ++mb) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((g * MB + mb) * N);
+            for (int tap = 0; tap < K; ++tap) {
+              const uint32_t a_row_off = (uint32_t)(mb * 128 + tap * dil);           // in 16 B units
+              const uint32_t b_tap_off = (uint32_t)tap * (uint32_t)(KC * N * 4 / 16);
+              for (int kk = 0; kk < KC / 8; ++kk) {
+                const uint32_t a_off = a_row_off + (uint32_t)(2 * kk) * (uint32_t)Rp;
+                const uint32_t b_off = b_tap_off + (uint32_t)(2 * kk) * (uint32_t)N;
+                const uint64_t a_hi = adesc0 + a_off, a_lo = adesc0 + a_off + (a_half >> 4);
+                const uint64_t b_hi = bdesc0 + b_off, b_lo = bdesc0 + b_off + (b_half >> 4);
+                const uint32_t first = (c == 0 && tap == 0 && kk == 0) ? 0u : 1u;
+                tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
+                tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+              }
+            }
+          }
+          tc_commit(bar_a_free + 8 * ab);
+          if (g == tiles - 1 && p.n_chunks > 1) tc_commit(bar_b_free + 8 * bb);
+        }
+        a_uses[ab] += 1;
+        a_count += 1;
+      }
+      if (load_b) b_loads[bb] += 1;
+      if (p.n_chunks > 1) b_count += 1;
+    }
+    // ---------------- accumulators complete -> fused epilogue
+    if (tid == 0) tc_commit(bar_acc);
+    mbar_wait(bar_acc, acc_count & 1);
+    acc_count += 1;
+    tc_fence_after();
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int ncol = N / 2;
+      for (int g = 0; g < tiles; ++g) {
+        for (int mb = 0; mb < MB; ++mb) {
+          const int t = t_group0 + g * MT + mb * 128 + q * 32 + lane;
+          const float msk = (t < len) ? 1.f : 0.f;
+          const uint32_t col0 = (uint32_t)((g * MB + mb) * N + half * ncol);
+          for (int cc = 0; cc < ncol; cc += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + col0 + cc, v);
+            const int co0 = nt * N + half * ncol + cc;
+            if (t >= T) {
+              // nothing to store for rows past the end (the warp still ran the aligned tcgen05.ld)
+            } else if (a.ep.mode == EPI_GATE) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) {
+                const int co = co0 + i;
+                if (co < a.Cout) {
+                  float ba, bbias;
+                  gate_terms(a, b, co, ba, bbias);
+                  gate_store(a, b, co, t, v[i] + ba, v[i + 1] + bbias);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int co = co0 + i;
+                if (co < a.Cout) epilogue_store(a, b, co, t, v[i] + channel_term(a, b, co), msk);
+              }
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ weight packing
+// dst[nt][chunk][hl][tap][kg][n][e] from the folded weight src[co][ci][tap]
+__global__ void pack_conv_tc_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ co_map,
+                                    const int* __restrict__ ci_map, int Cout, int Cin, int K, int src_cin, int N,
+                                    int n_tiles, int KC, int n_chunks) {
+  const long long per_half = (long long)K * KC * N;
+  const long long total = (long long)n_tiles * n_chunks * 2 * per_half;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int e = (int)(r % 4); r /= 4;
+    const int n = (int)(r % N); r /= N;
+    const int kg = (int)(r % (KC / 4)); r /= (KC / 4);
+    const int tap = (int)(r % K); r /= K;
+    const int hl = (int)(r % 2); r /= 2;
+    const int chunk = (int)(r % n_chunks); r /= n_chunks;
+    const int nt = (int)r;
+    const int co_p = nt * N + n, ci_p = chunk * KC + kg * 4 + e;
+    float w = 0.f;
+    if (co_p < Cout && ci_p < Cin) {
+      const int co = co_map[co_p];
+      const int ci = ci_map ? ci_map[ci_p] : ci_p;
+      if (co >= 0) w = src[((long long)co * src_cin + ci) * K + tap];
+    }
+    const float hi = tf32_rna(w);
+    dst[i] = hl ? tf32_rna(w - hi) : hi;
+  }
+}
+
+}  // namespace
+
+size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_bbuf) {
+  const int R = 128 * MB + (K - 1) * dil;
+  const int Rp = (R + 7) & ~7;
+  return 128 + 2 * (size_t)(2 * KC * Rp * 4) + (size_t)n_bbuf * (2 * (size_t)K * KC * N * 4);
+}
+
+bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
+  if (Cin < 8 || Cout < 16) return false;
+  const size_t budget = 220 * 1024;
+  const int cout32 = (Cout + 31) / 32 * 32;
+  const int n_tiles = (cout32 + 255) / 256;
+  const int N = ((cout32 + n_tiles - 1) / n_tiles + 31) / 32 * 32;
+  const int cin8 = (Cin + 7) / 8 * 8;
+  for (int MB = 2; MB >= 1; --MB) {
+    if (MB * N > 512) continue;
+    for (int nch = 1; nch <= cin8 / 8; ++nch) {
+      const int KC = ((cin8 + nch - 1) / nch + 7) / 8 * 8;
+      const int nb = nch == 1 ? 1 : 2;
+      if ((size_t)tc_conv_smem_bytes(K, dil, N, KC, MB, nb) <= budget) {
+        const int R = 128 * MB + (K - 1) * dil;
+        plan->N = N; plan->n_tiles = n_tiles; plan->KC = KC; plan->n_chunks = (cin8 + KC - 1) / KC;
+        plan->MB = MB; plan->G = 512 / (MB * N); plan->n_bbuf = plan->n_chunks == 1 ? 1 : 2;
+        plan->R_pad = (R + 7) & ~7; plan->dil = dil;
+        plan->packed_floats = (size_t)n_tiles * plan->n_chunks * 2 * K * KC * N;
+        return true;
+      }
+    }
+  }
+  return false;
+}
+
+void launch_pack_conv_tc(const float* src, float* dst, const int* co_map, const int* ci_map, int Cout, int Cin, int K,
+                         int src_cin, const TcPlan& pl, cudaStream_t s) {
+  const long long total = (long long)pl.packed_floats;
+  const int blocks = (int)((total + 255) / 256 > 8192 ? 8192 : (total + 255) / 256);
+  pack_conv_tc_kernel<<<blocks, 256, 0, s>>>(src, dst, co_map, ci_map, Cout, Cin, K, src_cin, pl.N, pl.n_tiles, pl.KC,
+                                             pl.n_chunks);
+  count_launch();
+}
+
+static bool g_tc_enabled = true;
+void set_tensor_cores_enabled(bool on) { g_tc_enabled = on; }
+bool tensor_cores_enabled() { return g_tc_enabled; }
+
+void launch_conv1d_tc(const ConvArgs& a, cudaStream_t s) {
+  const TcPlan& pl = a.tc;
+  TcConvArgs p;
+  p.c = a;
+  p.wtc = a.wtc;
+  // the packed layout depends on (N, KC, n_chunks) only; M-blocks per tile are chosen per launch
+  const int MB = (a.T > 128 && pl.MB == 2) ? 2 : 1;
+  const int R = 128 * MB + (a.K - 1) * a.dil;
+  p.N = pl.N; p.n_tiles = pl.n_tiles; p.KC = pl.KC; p.n_chunks = pl.n_chunks; p.MB = MB; p.G = 512 / (MB * pl.N);
+  p.n_bbuf = pl.n_bbuf; p.R_pad = (R + 7) & ~7;
+  const size_t smem = tc_conv_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, pl.n_bbuf);
+  static size_t configured = 0;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (smem > configured) {
+    cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  const int group_rows = p.G * 128 * MB;
+  const long long items = (long long)a.B * ((a.T + group_rows - 1) / group_rows) * pl.n_tiles;
+  const int grid = (int)(items < n_sm ? items : n_sm);
+  conv1d_tc_kernel<<<grid, kTcThreads, smem, s>>>(p);
+  count_launch();
+}
+
+}  // namespace wetts
