@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -210,6 +211,10 @@ struct wetts_vits_s {
     }
     c->wtc = nullptr;
     if (tc_dil > 0 && tc_conv_plan(c->Cin, c->Cout, K, tc_dil, &c->tc)) {
+      if (getenv("WETTS_DEBUG_PLAN"))
+        fprintf(stderr, "[tc plan] Cin=%d Cout=%d K=%d dil=%d -> mode=%d N=%d n_tiles=%d KC=%d chunks=%d MB=%d G=%d abuf=%d bbuf=%d smem=%zu\n",
+                c->Cin, c->Cout, K, tc_dil, c->tc.mode, c->tc.N, c->tc.n_tiles, c->tc.KC, c->tc.n_chunks, c->tc.MB, c->tc.G,
+                c->tc.n_abuf, c->tc.n_bbuf, tc_conv_smem_bytes(K, tc_dil, c->tc.N, c->tc.KC, c->tc.MB, c->tc.n_abuf, c->tc.n_bbuf));
       if (dalloc(&c->wtc, c->tc.packed_floats)) return 1;
       launch_pack_conv_tc(w.d, c->wtc, d_co, d_ci, c->Cout, c->Cin, K, src_cin, c->tc, 0);
     }

@@ -14,8 +14,41 @@ __device__ __forceinline__ float channel_term(const ConvArgs& a, int b, int co) 
   return bv;
 }
 
+// Epilogues are split in two phases so a thread can issue the global loads of many outputs
+// back to back (memory-level parallelism) before any dependent store: epilogue_load() only
+// reads, epilogue_finish() computes and writes.
+struct EpiLoad {
+  float a = 0.f, b = 0.f;
+};
+
+__device__ __forceinline__ EpiLoad epilogue_load(const ConvArgs& a, int b, int co, int t) {
+  const ConvEpilogue& e = a.ep;
+  EpiLoad l;
+  const long long off = (long long)b * e.out_bs + (long long)co * a.T + t;
+  switch (e.mode) {
+    case EPI_RESID:
+      l.a = e.resid[off];
+      break;
+    case EPI_MRF:
+      l.a = e.resid[off];
+      if (e.acc_mode != 0) l.b = e.out[off];
+      break;
+    case EPI_RES_SKIP:
+      if (!e.last && co < e.H) l.a = e.x[off];
+      else if (!e.skip_init) l.a = e.skip[(long long)b * e.out_bs + (long long)(e.last ? co : co - e.H) * a.T + t];
+      break;
+    case EPI_COUPLING:
+      l.a = e.out[(long long)b * e.out_bs + (long long)(e.z_c0 + co * e.z_cstep) * a.T + t];
+      break;
+    default:
+      break;
+  }
+  return l;
+}
+
 // v already contains the bias term
-__device__ __forceinline__ void epilogue_store(const ConvArgs& a, int b, int co, int t, float v, float msk) {
+__device__ __forceinline__ void epilogue_finish(const ConvArgs& a, int b, int co, int t, float v, float msk,
+                                                const EpiLoad& l) {
   const ConvEpilogue& e = a.ep;
   const int T = a.T;
   const long long off = (long long)b * e.out_bs + (long long)co * T + t;
@@ -26,34 +59,36 @@ __device__ __forceinline__ void epilogue_store(const ConvArgs& a, int b, int co,
       e.out[off] = v;
       break;
     case EPI_RESID:
-      e.out[off] = v + e.resid[off];
+      e.out[off] = v + l.a;
       break;
     case EPI_MRF: {
-      v += e.resid[off];
+      v += l.a;
       if (e.acc_mode == 0) e.out[off] = v;
-      else if (e.acc_mode == 1) e.out[off] = e.out[off] + v;
-      else e.out[off] = (e.out[off] + v) / e.div;
+      else if (e.acc_mode == 1) e.out[off] = l.b + v;
+      else e.out[off] = (l.b + v) / e.div;
       break;
     }
     case EPI_RES_SKIP: {
       if (!e.last && co < e.H) {
-        e.x[off] = (e.x[off] + v) * msk;
+        e.x[off] = (l.a + v) * msk;
       } else {
         const int c2 = e.last ? co : co - e.H;
-        const long long o2 = (long long)b * e.out_bs + (long long)c2 * T + t;
-        e.skip[o2] = e.skip_init ? v : e.skip[o2] + v;
+        e.skip[(long long)b * e.out_bs + (long long)c2 * T + t] = e.skip_init ? v : l.a + v;
       }
       break;
     }
     case EPI_COUPLING: {
       const int zc = e.z_c0 + co * e.z_cstep;
-      float* p = e.out + (long long)b * e.out_bs + (long long)zc * T + t;
-      *p = (*p - v * msk) * msk;
+      e.out[(long long)b * e.out_bs + (long long)zc * T + t] = (l.a - v * msk) * msk;
       break;
     }
     default:
       break;
   }
+}
+
+__device__ __forceinline__ void epilogue_store(const ConvArgs& a, int b, int co, int t, float v, float msk) {
+  epilogue_finish(a, b, co, t, v, msk, epilogue_load(a, b, co, t));
 }
 
 // EPI_GATE: packed channels (co, co+1) = (tanh half j, sigmoid half j), j = co/2

@@ -38,7 +38,8 @@ struct ConvEpilogue {
 
 // tiling of the tcgen05 implicit-GEMM path (tc_conv_kernel.cu), fixed per conv at load time
 struct TcPlan {
-  int N = 0, n_tiles = 0, KC = 0, n_chunks = 0, MB = 0, G = 0, n_bbuf = 0, R_pad = 0, dil = 1;
+  int mode = 0, N = 0, n_tiles = 0, KC = 0, n_chunks = 0, MB = 0, G = 0, n_abuf = 2, n_bbuf = 0, R_pad = 0, dil = 1;
+  int tmem_cols = 512;
   size_t packed_floats = 0;
 };
 
@@ -63,10 +64,10 @@ void launch_conv1d_simt(const ConvArgs& a, cudaStream_t s);
 struct TcConvArgs {
   ConvArgs c;
   const float* wtc;
-  int N, n_tiles, KC, n_chunks, MB, G, n_bbuf, R_pad;
+  int N, n_tiles, KC, n_chunks, MB, G, n_abuf, n_bbuf, R_pad, tmem_cols;
 };
 bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan);
-size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_bbuf);
+size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_abuf, int n_bbuf);
 void launch_pack_conv_tc(const float* src, float* dst, const int* co_map, const int* ci_map, int Cout, int Cin, int K,
                          int src_cin, const TcPlan& pl, cudaStream_t s);
 void launch_conv1d_tc(const ConvArgs& a, cudaStream_t s);

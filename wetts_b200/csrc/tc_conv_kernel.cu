@@ -26,8 +26,6 @@
 namespace wetts {
 namespace {
 
-constexpr int kTcThreads = 256;
-constexpr uint32_t kTmemCols = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -96,7 +94,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvArgs p) {
+// THREADS = 256 with 2 CTAs/SM (256 TMEM columns each) for layers whose weight tile fits beside the
+// activation tile in ~110 KB, else 512 threads, 1 CTA/SM, 512 columns.  In both cases a CTA is a
+// persistent worker: stage (global -> regs -> split -> smem), issue MMAs (async), prefetching
+// epilogue; the asynchronous tensor pipe and the second CTA hide each other's memory phases.
+template <int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcConvArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& a = p.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -108,12 +111,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
   const uint32_t a_bytes = 2 * a_half;
   const uint32_t b_half = (uint32_t)K * KC * N * 4;    // bytes of one hi or lo weight tile
   const uint32_t b_bytes = 2 * b_half;
-  const int nb = p.n_bbuf;
+  const int nb = p.n_bbuf, na = p.n_abuf;
+  const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
   uint8_t* A0 = smem + 128;
-  uint8_t* B0 = A0 + 2 * a_bytes;
+  uint8_t* B0 = A0 + (size_t)na * a_bytes;
   const uint32_t bar_a_free = smem_u32(&bars[0]);   // [2]
   const uint32_t bar_b_full = smem_u32(&bars[2]);   // [2]
   const uint32_t bar_b_free = smem_u32(&bars[4]);   // [2]
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(kTmemCols)
+                 "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -142,11 +146,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
   const int items_per_nt = a.B * n_groups;
   const int n_items = items_per_nt * p.n_tiles;
 
-  uint32_t a_uses[2] = {0, 0};       // completed stagings per A buffer
-  uint32_t b_loads[2] = {0, 0};      // loads issued per B buffer
+  uint32_t a_uses0 = 0, a_uses1 = 0;   // stagings issued per A buffer
+  uint32_t b_loads0 = 0, b_loads1 = 0; // loads issued per B buffer
   uint32_t acc_count = 0;
-  int b_resident_nt = -1;            // weight tile resident in B[0] (single-chunk layers)
+  int b_resident_nt = -1;              // weight tile resident in B[0] (single-chunk layers)
   uint32_t a_count = 0, b_count = 0;
+  const int nb16 = (KC + 15) / 16;
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int nt = item / items_per_nt;
@@ -168,10 +173,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
       } else {
         bb = (nb == 2) ? (int)(b_count & 1) : 0;
       }
+      const uint32_t b_loads = bb ? b_loads1 : b_loads0;
       if (load_b) {
         // multi-chunk layers: the MMAs that last read this buffer committed to b_free; single-chunk
         // layers reload only across work items, whose MMAs the accumulator barrier already covered
-        if (p.n_chunks > 1 && b_loads[bb] > 0) mbar_wait(bar_b_free + 8 * bb, (b_loads[bb] - 1) & 1);
+        if (p.n_chunks > 1 && b_loads > 0) mbar_wait(bar_b_free + 8 * bb, (b_loads - 1) & 1);
         if (tid == 0) {
           const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + c) * b_bytes;
           mbar_expect_tx(bar_b_full + 8 * bb, b_bytes);
@@ -185,45 +191,56 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
       }
       const int c0 = c * KC;
       for (int g = 0; g < tiles; ++g) {
-        const int ab = (int)(a_count & 1);
-        if (a_uses[ab] > 0) mbar_wait(bar_a_free + 8 * ab, (a_uses[ab] - 1) & 1);
-        // ---------------- stage activations: rows [t_tile0 - pad, +R), channels [c0, c0+KC)
+        const int ab = (na == 2) ? (int)(a_count & 1) : 0;
+        const uint32_t a_uses = ab ? a_uses1 : a_uses0;
+        // ---------------- stage activations: rows [t_tile0 - pad, +R), channels [c0, c0+KC):
+        // 16 independent global loads per thread are in flight before the first dependent use
         {
-          uint8_t* Ah = A0 + ab * a_bytes;
+          uint8_t* Ah = A0 + (size_t)ab * a_bytes;
           const int t_in0 = t_group0 + g * MT - a.pad_left;
-          for (int cg = 0; cg < KC / 4; ++cg) {
-            const int ci0 = c0 + cg * 4;
-            const float* src = in_b + (long long)ci0 * a.in_cs;
-            float4* dst_hi = reinterpret_cast<float4*>(Ah + (size_t)cg * Rp * 16);
-            float4* dst_lo = reinterpret_cast<float4*>(Ah + a_half + (size_t)cg * Rp * 16);
-            for (int r = tid; r < Rp; r += kTcThreads) {
-              const int t = t_in0 + r;
-              float v[4] = {0.f, 0.f, 0.f, 0.f};
-              if (r < R && t >= 0 && t < t_hi) {
+          bool waited = (a_uses == 0);
+          for (int idx = tid; idx < Rp * nb16; idx += THREADS) {
+            const int q16 = idx / Rp, r = idx - q16 * Rp;
+            const int t = t_in0 + r;
+            const bool rok = (r < R) && (t >= 0) && (t < t_hi);
+            const int ci0 = c0 + q16 * 16;
+            const float* src = in_b + (long long)ci0 * a.in_cs + t;
+            float v[16];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  if (ci0 + e < a.Cin) {
-                    float x = __ldg(src + (long long)e * a.in_cs + t);
-                    if (a.pre_act) x = x > 0.f ? x : x * a.pre_slope;
-                    v[e] = x;
-                  }
+            for (int e = 0; e < 16; ++e) {
+              v[e] = 0.f;
+              if (rok && (ci0 + e) < a.Cin && (q16 * 16 + e) < KC) v[e] = __ldg(src + (long long)e * a.in_cs);
+            }
+            if (!waited) {  // the MMAs that read this buffer last must be done before we overwrite it
+              mbar_wait(bar_a_free + 8 * ab, (a_uses - 1) & 1);
+              waited = true;
+            }
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) {
+              if (q16 * 16 + cg * 4 < KC) {
+                float4 hi, lo;
+                float x0 = v[cg * 4 + 0], x1 = v[cg * 4 + 1], x2 = v[cg * 4 + 2], x3 = v[cg * 4 + 3];
+                if (a.pre_act) {
+                  x0 = x0 > 0.f ? x0 : x0 * a.pre_slope; x1 = x1 > 0.f ? x1 : x1 * a.pre_slope;
+                  x2 = x2 > 0.f ? x2 : x2 * a.pre_slope; x3 = x3 > 0.f ? x3 : x3 * a.pre_slope;
                 }
+                hi.x = tf32_rna(x0); lo.x = tf32_rna(x0 - hi.x);
+                hi.y = tf32_rna(x1); lo.y = tf32_rna(x1 - hi.y);
+                hi.z = tf32_rna(x2); lo.z = tf32_rna(x2 - hi.z);
+                hi.w = tf32_rna(x3); lo.w = tf32_rna(x3 - hi.w);
+                const size_t o = ((size_t)(q16 * 4 + cg) * Rp + r) * 16;
+                *reinterpret_cast<float4*>(Ah + o) = hi;
+                *reinterpret_cast<float4*>(Ah + a_half + o) = lo;
               }
-              float4 hi, lo;
-              hi.x = tf32_rna(v[0]); lo.x = tf32_rna(v[0] - hi.x);
-              hi.y = tf32_rna(v[1]); lo.y = tf32_rna(v[1] - hi.y);
-              hi.z = tf32_rna(v[2]); lo.z = tf32_rna(v[2] - hi.z);
-              hi.w = tf32_rna(v[3]); lo.w = tf32_rna(v[3] - hi.w);
-              dst_hi[r] = hi;
-              dst_lo[r] = lo;
             }
           }
+          if (!waited) mbar_wait(bar_a_free + 8 * ab, (a_uses - 1) & 1);
         }
         fence_async_smem();
         __syncthreads();
         // ---------------- issue the MMAs of (tile g, chunk c)
         if (tid == 0) {
-          if (load_b && g == 0) mbar_wait(bar_b_full + 8 * bb, b_loads[bb] & 1);
+          if (load_b && g == 0) mbar_wait(bar_b_full + 8 * bb, b_loads & 1);
           tc_fence_after();
           const uint64_t adesc0 = make_desc(A_addr + ab * a_bytes, (uint32_t)Rp * 16, 128);
           const uint64_t bdesc0 = make_desc(B_addr + bb * b_bytes, (uint32_t)N * 16, 128);
@@ -247,10 +264,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
           tc_commit(bar_a_free + 8 * ab);
           if (g == tiles - 1 && p.n_chunks > 1) tc_commit(bar_b_free + 8 * bb);
         }
-        a_uses[ab] += 1;
+        if (ab) a_uses1 += 1; else a_uses0 += 1;
         a_count += 1;
       }
-      if (load_b) b_loads[bb] += 1;
+      if (load_b) { if (bb) b_loads1 += 1; else b_loads0 += 1; }
       if (p.n_chunks > 1) b_count += 1;
     }
     // ---------------- accumulators complete -> fused epilogue
@@ -259,17 +276,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
     acc_count += 1;
     tc_fence_after();
     {
-      const int q = warp & 3, half = warp >> 2;
-      const int ncol = N / 2;
+      constexpr int COLSPLIT = THREADS / 128;     // warps sharing a TMEM lane quarter split the columns
+      const int q = warp & 3, part = warp >> 2;
+      const int ncol = N / COLSPLIT;
       for (int g = 0; g < tiles; ++g) {
         for (int mb = 0; mb < MB; ++mb) {
           const int t = t_group0 + g * MT + mb * 128 + q * 32 + lane;
           const float msk = (t < len) ? 1.f : 0.f;
-          const uint32_t col0 = (uint32_t)((g * MB + mb) * N + half * ncol);
+          const uint32_t col0 = (uint32_t)((g * MB + mb) * N + part * ncol);
           for (int cc = 0; cc < ncol; cc += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + col0 + cc, v);
-            const int co0 = nt * N + half * ncol + cc;
+            const int co0 = nt * N + part * ncol + cc;
             if (t >= T) {
               // nothing to store for rows past the end (the warp still ran the aligned tcgen05.ld)
             } else if (a.ep.mode == EPI_GATE) {
@@ -283,10 +301,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
                 }
               }
             } else {
+              EpiLoad l[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (co0 + i < a.Cout) l[i] = epilogue_load(a, b, co0 + i, t);
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
                 const int co = co0 + i;
-                if (co < a.Cout) epilogue_store(a, b, co, t, v[i] + channel_term(a, b, co), msk);
+                if (co < a.Cout) epilogue_finish(a, b, co, t, v[i] + channel_term(a, b, co), msk, l[i]);
               }
             }
           }
@@ -299,7 +321,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv1d_tc_kernel(const TcConvAr
   }
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -333,31 +355,53 @@ __global__ void pack_conv_tc_kernel(const float* __restrict__ src, float* __rest
 
 }  // namespace
 
-size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_bbuf) {
+size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_abuf, int n_bbuf) {
   const int R = 128 * MB + (K - 1) * dil;
   const int Rp = (R + 7) & ~7;
-  return 128 + 2 * (size_t)(2 * KC * Rp * 4) + (size_t)n_bbuf * (2 * (size_t)K * KC * N * 4);
+  return 128 + (size_t)n_abuf * (2 * (size_t)KC * Rp * 4) + (size_t)n_bbuf * (2 * (size_t)K * KC * N * 4);
 }
 
+// Chooses the tiling.  mode 0 ("small"): <= 110 KB shared memory, 256 TMEM columns, 256 threads, two CTAs per
+// SM, only if the whole C_in fits one chunk (weights then stay resident in the persistent CTA).  Otherwise
+// mode 1 ("large"): <= 220 KB, 512 columns, 512 threads, one CTA per SM, C_in chunked with double-buffered
+// weight tiles.
 bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
   if (Cin < 8 || Cout < 16) return false;
-  const size_t budget = 220 * 1024;
-  const int cout32 = (Cout + 31) / 32 * 32;
-  const int n_tiles = (cout32 + 255) / 256;
-  const int N = ((cout32 + n_tiles - 1) / n_tiles + 31) / 32 * 32;
   const int cin8 = (Cin + 7) / 8 * 8;
-  for (int MB = 2; MB >= 1; --MB) {
-    if (MB * N > 512) continue;
-    for (int nch = 1; nch <= cin8 / 8; ++nch) {
-      const int KC = ((cin8 + nch - 1) / nch + 7) / 8 * 8;
-      const int nb = nch == 1 ? 1 : 2;
-      if ((size_t)tc_conv_smem_bytes(K, dil, N, KC, MB, nb) <= budget) {
-        const int R = 128 * MB + (K - 1) * dil;
-        plan->N = N; plan->n_tiles = n_tiles; plan->KC = KC; plan->n_chunks = (cin8 + KC - 1) / KC;
-        plan->MB = MB; plan->G = 512 / (MB * N); plan->n_bbuf = plan->n_chunks == 1 ? 1 : 2;
-        plan->R_pad = (R + 7) & ~7; plan->dil = dil;
-        plan->packed_floats = (size_t)n_tiles * plan->n_chunks * 2 * K * KC * N;
-        return true;
+  const int cout32 = (Cout + 31) / 32 * 32;
+  auto fill = [&](int mode, int N, int n_tiles, int KC, int MB, int na, int nb) {
+    const int R = 128 * MB + (K - 1) * dil;
+    plan->mode = mode; plan->N = N; plan->n_tiles = n_tiles; plan->KC = KC; plan->n_chunks = (cin8 + KC - 1) / KC;
+    plan->MB = MB; plan->tmem_cols = mode == 0 ? 256 : 512; plan->G = plan->tmem_cols / (MB * N);
+    plan->n_abuf = na; plan->n_bbuf = nb; plan->R_pad = (R + 7) & ~7; plan->dil = dil;
+    plan->packed_floats = (size_t)n_tiles * plan->n_chunks * 2 * K * KC * N;
+  };
+  // ---- small mode
+  if (cout32 <= 128) {
+    const int N = cout32;
+    for (int na = 2; na >= 1; --na)
+      for (int MB = 2; MB >= 1; --MB) {
+        if (MB * N > 256) continue;
+        if (tc_conv_smem_bytes(K, dil, N, cin8, MB, na, 1) <= 110 * 1024) {
+          fill(0, N, 1, cin8, MB, na, 1);
+          return true;
+        }
+      }
+  }
+  // ---- large mode (N a multiple of 64 so that 16 warps split the columns in 16-wide pieces); prefer the
+  // widest N tile, fall back to narrower tiles when the weight tile of one tap does not fit
+  const int cout64 = (Cout + 63) / 64 * 64;
+  for (int n_tiles = (cout64 + 255) / 256; n_tiles <= cout64 / 64; ++n_tiles) {
+    const int N = ((cout64 + n_tiles - 1) / n_tiles + 63) / 64 * 64;
+    for (int MB = 2; MB >= 1; --MB) {
+      if (MB * N > 512) continue;
+      for (int nch = 1; nch <= cin8 / 8; ++nch) {
+        const int KC = ((cin8 + nch - 1) / nch + 7) / 8 * 8;
+        const int nb = (cin8 + KC - 1) / KC == 1 ? 1 : 2;
+        if (tc_conv_smem_bytes(K, dil, N, KC, MB, 2, nb) <= 220 * 1024) {
+          fill(1, N, n_tiles, KC, MB, 2, nb);
+          return true;
+        }
       }
     }
   }
@@ -385,24 +429,34 @@ void launch_conv1d_tc(const ConvArgs& a, cudaStream_t s) {
   // the packed layout depends on (N, KC, n_chunks) only; M-blocks per tile are chosen per launch
   const int MB = (a.T > 128 && pl.MB == 2) ? 2 : 1;
   const int R = 128 * MB + (a.K - 1) * a.dil;
-  p.N = pl.N; p.n_tiles = pl.n_tiles; p.KC = pl.KC; p.n_chunks = pl.n_chunks; p.MB = MB; p.G = 512 / (MB * pl.N);
-  p.n_bbuf = pl.n_bbuf; p.R_pad = (R + 7) & ~7;
-  const size_t smem = tc_conv_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, pl.n_bbuf);
-  static size_t configured = 0;
+  p.N = pl.N; p.n_tiles = pl.n_tiles; p.KC = pl.KC; p.n_chunks = pl.n_chunks; p.MB = MB;
+  p.tmem_cols = pl.tmem_cols; p.G = pl.tmem_cols / (MB * pl.N);
+  p.n_abuf = pl.n_abuf; p.n_bbuf = pl.n_bbuf; p.R_pad = (R + 7) & ~7;
+  const size_t smem = tc_conv_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, pl.n_abuf, pl.n_bbuf);
+  static size_t configured[2] = {0, 0};
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
-  if (smem > configured) {
-    cudaFuncSetAttribute(conv1d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   const int group_rows = p.G * 128 * MB;
   const long long items = (long long)a.B * ((a.T + group_rows - 1) / group_rows) * pl.n_tiles;
-  const int grid = (int)(items < n_sm ? items : n_sm);
-  conv1d_tc_kernel<<<grid, kTcThreads, smem, s>>>(p);
+  if (pl.mode == 0) {
+    if (smem > configured[0]) {
+      cudaFuncSetAttribute(conv1d_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured[0] = smem;
+    }
+    const int grid = (int)(items < 2 * n_sm ? items : 2 * n_sm);
+    conv1d_tc_kernel<256, 2><<<grid, 256, smem, s>>>(p);
+  } else {
+    if (smem > configured[1]) {
+      cudaFuncSetAttribute(conv1d_tc_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured[1] = smem;
+    }
+    const int grid = (int)(items < n_sm ? items : n_sm);
+    conv1d_tc_kernel<512, 1><<<grid, 512, smem, s>>>(p);
+  }
   count_launch();
 }
 
