@@ -94,12 +94,119 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-// THREADS = 256 with 2 CTAs/SM (256 TMEM columns each) for layers whose weight tile fits beside the
-// activation tile in ~110 KB, else 512 threads, 1 CTA/SM, 512 columns.  In both cases a CTA is a
-// persistent worker: stage (global -> regs -> split -> smem), issue MMAs (async), prefetching
-// epilogue; the asynchronous tensor pipe and the second CTA hide each other's memory phases.
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_with_lo(uint64_t base, uint32_t lo) {
+  return (base & 0xFFFFFFFF00000000ull) | (uint64_t)lo;
+}
+
+// Fused epilogue of one 16-channel slice of one output row, specialised per mode with the switch
+// hoisted out of the element loops: all global loads of the slice are issued before the first store.
+// v[i] already contains bias (+ conditioning).
+__device__ __forceinline__ void tc_epilogue_slice(const ConvArgs& a, int b, int t, int co0, float* v, float msk) {
+  const ConvEpilogue& e = a.ep;
+  const size_t Ts = (size_t)a.T;
+  const size_t row = (size_t)b * (size_t)e.out_bs + (size_t)t;
+  const int nval = min(16, a.Cout - co0);
+  switch (e.mode) {
+    case EPI_PLAIN: {
+      float* op = e.out + row + (size_t)co0 * Ts;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = v[i];
+        if (e.act == 1) x = fmaxf(x, 0.f);
+        if (e.out_mask) x *= msk;
+        if (i < nval) op[(size_t)i * Ts] = x;
+      }
+      break;
+    }
+    case EPI_RESID: {
+      const float* rp = e.resid + row + (size_t)co0 * Ts;
+      float* op = e.out + row + (size_t)co0 * Ts;
+      float r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? rp[(size_t)i * Ts] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nval) op[(size_t)i * Ts] = v[i] + r[i];
+      break;
+    }
+    case EPI_MRF: {
+      const float* rp = e.resid + row + (size_t)co0 * Ts;
+      float* op = e.out + row + (size_t)co0 * Ts;
+      float r[16], o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? rp[(size_t)i * Ts] : 0.f;
+      if (e.acc_mode != 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = (i < nval) ? op[(size_t)i * Ts] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = v[i] + r[i];
+        if (e.acc_mode == 1) x = o[i] + x;
+        else if (e.acc_mode == 2) x = (o[i] + x) / e.div;
+        if (i < nval) op[(size_t)i * Ts] = x;
+      }
+      break;
+    }
+    case EPI_GATE: {
+      float* op = e.out + row + (size_t)(co0 >> 1) * Ts;
+#pragma unroll
+      for (int i = 0; i < 16; i += 2)
+        if (i < nval) op[(size_t)(i >> 1) * Ts] = tanhf(v[i]) * sigmoidf_acc(v[i + 1]);
+      break;
+    }
+    case EPI_RES_SKIP: {
+      if (!e.last && co0 < e.H) {  // residual stream (a 16-slice never straddles H: H % 16 == 0 is checked on the host)
+        float* xp = e.x + row + (size_t)co0 * Ts;
+        float r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? xp[(size_t)i * Ts] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nval) xp[(size_t)i * Ts] = (r[i] + v[i]) * msk;
+      } else {
+        float* sp = e.skip + row + (size_t)(e.last ? co0 : co0 - e.H) * Ts;
+        float r[16];
+        if (!e.skip_init) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? sp[(size_t)i * Ts] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nval) sp[(size_t)i * Ts] = e.skip_init ? v[i] : r[i] + v[i];
+      }
+      break;
+    }
+    case EPI_COUPLING: {
+      float* zp = e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts;
+      const long long step = (long long)e.z_cstep * (long long)Ts;
+      float r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? zp[(long long)i * step] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nval) zp[(long long)i * step] = (r[i] - v[i] * msk) * msk;
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+// Warp-specialised persistent kernel with THREADS threads (8 or 16 warps).  The last warp owns the
+// tensor pipe during the main loop: one elected lane issues the weight bulk copies and every
+// tcgen05.mma / tcgen05.commit; the other warps stage activations.  The roles meet only at mbarriers
+// (a_full / a_free per activation buffer, b_full / b_free per weight buffer, acc per work item) --
+// there is no CTA-wide barrier inside an item, so staging of the next tile, the MMAs of the current
+// one and other warps' loads overlap.  All warps then share the epilogue.
+// THREADS = 256 runs 2 CTAs/SM (256 TMEM columns each), THREADS = 512 one CTA/SM (512 columns).
 template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcConvArgs p) {
+  constexpr int STAGERS = THREADS - 32;   // threads that stage activations
+  constexpr int MMA_WARP = THREADS / 32 - 1;
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& a = p.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -115,13 +222,15 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
   const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
-  uint8_t* A0 = smem + 128;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 96);
+  float* addv = reinterpret_cast<float*>(smem + 128);  // [2][N] bias + conditioning of the current item
+  uint8_t* A0 = smem + 128 + 2 * 256 * 4;
   uint8_t* B0 = A0 + (size_t)na * a_bytes;
-  const uint32_t bar_a_free = smem_u32(&bars[0]);   // [2]
-  const uint32_t bar_b_full = smem_u32(&bars[2]);   // [2]
-  const uint32_t bar_b_free = smem_u32(&bars[4]);   // [2]
-  const uint32_t bar_acc = smem_u32(&bars[6]);
+  const uint32_t bar_a_free = smem_u32(&bars[0]);   // [2]  MMA -> workers: activation buffer reusable
+  const uint32_t bar_b_full = smem_u32(&bars[2]);   // [2]  TMA -> MMA: weight tile landed
+  const uint32_t bar_b_free = smem_u32(&bars[4]);   // [2]  MMA -> MMA: weight buffer reusable
+  const uint32_t bar_acc = smem_u32(&bars[6]);      //      MMA -> workers: accumulators complete
+  const uint32_t bar_a_full = smem_u32(&bars[8]);   // [2]  workers -> MMA: activation tile staged
   const uint32_t A_addr = smem_u32(A0), B_addr = smem_u32(B0);
 
   if (warp == 0) {
@@ -132,6 +241,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
   }
   if (tid == 0) {
     for (int i = 0; i < 7; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    mbar_init(bar_a_full, STAGERS / 32);
+    mbar_init(bar_a_full + 8, STAGERS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -139,19 +250,21 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
   const int G = p.G;
   const int group_rows = G * MT;
   const int n_groups = (T + group_rows - 1) / group_rows;
   const int items_per_nt = a.B * n_groups;
   const int n_items = items_per_nt * p.n_tiles;
 
-  uint32_t a_uses0 = 0, a_uses1 = 0;   // stagings issued per A buffer
-  uint32_t b_loads0 = 0, b_loads1 = 0; // loads issued per B buffer
-  uint32_t acc_count = 0;
-  int b_resident_nt = -1;              // weight tile resident in B[0] (single-chunk layers)
-  uint32_t a_count = 0, b_count = 0;
+  // role-private pipeline state
+  uint32_t a_fills0 = 0, a_fills1 = 0, b_loads0 = 0, b_loads1 = 0, b_count = 0;   // MMA lane
+  int b_resident_nt = -1;
+  uint32_t a_uses0 = 0, a_uses1 = 0;                                              // stagers
+  uint32_t a_count = 0, acc_count = 0, item_count = 0;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t a_lo_delta = a_half >> 4, b_lo_delta = b_half >> 4;
   const int nb16 = (KC + 15) / 16;
+  const bool full16 = (KC % 16 == 0);
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int nt = item / items_per_nt;
@@ -160,64 +273,127 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
     const int t_group0 = (rem - b * n_groups) * group_rows;
     const int tiles = min(G, (T - t_group0 + MT - 1) / MT);
     const long long len = a.lengths ? a.lengths[b] : (long long)T;
-    const int t_hi = a.in_mask ? (int)(len < T ? len : T) : T;
-    const float* in_b = a.in + (long long)b * a.in_bs;
-
-    for (int c = 0; c < p.n_chunks; ++c) {
-      // ---------------- weights for (nt, c)
-      int bb = 0;
-      bool load_b = true;
-      if (p.n_chunks == 1) {
-        load_b = (b_resident_nt != nt);
-        b_resident_nt = nt;
-      } else {
-        bb = (nb == 2) ? (int)(b_count & 1) : 0;
-      }
-      const uint32_t b_loads = bb ? b_loads1 : b_loads0;
-      if (load_b) {
-        // multi-chunk layers: the MMAs that last read this buffer committed to b_free; single-chunk
-        // layers reload only across work items, whose MMAs the accumulator barrier already covered
-        if (p.n_chunks > 1 && b_loads > 0) mbar_wait(bar_b_free + 8 * bb, (b_loads - 1) & 1);
-        if (tid == 0) {
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + c) * b_bytes;
-          mbar_expect_tx(bar_b_full + 8 * bb, b_bytes);
-          uint32_t off = 0;
-          while (off < b_bytes) {
-            const uint32_t n = min(b_bytes - off, 32768u);
-            bulk_g2s(B_addr + bb * b_bytes + off, src + off, n, bar_b_full + 8 * bb);
-            off += n;
-          }
+    // per-item additive term of every output channel (bias + speaker conditioning), double buffered
+    float* av = addv + (item_count & 1) * 256;
+    for (int n = tid; n < N; n += THREADS) {
+      const int co = nt * N + n;
+      float x = 0.f;
+      if (co < a.Cout) {
+        if (a.bias) x = a.bias[co];
+        if (a.ep.cond) {
+          const float* gp = a.ep.cond + (long long)b * a.ep.cond_bs + a.ep.cond_off;
+          if (a.ep.mode == EPI_GATE) x += (co & 1) ? gp[a.ep.H + (co >> 1)] : gp[co >> 1];
+          else if (a.ep.mode == EPI_PLAIN) x += gp[co];
         }
       }
-      const int c0 = c * KC;
-      for (int g = 0; g < tiles; ++g) {
-        const int ab = (na == 2) ? (int)(a_count & 1) : 0;
-        const uint32_t a_uses = ab ? a_uses1 : a_uses0;
-        // ---------------- stage activations: rows [t_tile0 - pad, +R), channels [c0, c0+KC):
-        // 16 independent global loads per thread are in flight before the first dependent use
-        {
+      av[n] = x;
+    }
+    item_count += 1;
+    // the previous item's TMEM reads (all warps) are ordered before this item's first MMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == MMA_WARP) {
+      // =========================== tensor-pipe warp (one elected lane) ===========================
+      if (lane == 0) {
+        for (int c = 0; c < p.n_chunks; ++c) {
+          int bb = 0;
+          bool load_b = true;
+          if (p.n_chunks == 1) {
+            load_b = (b_resident_nt != nt);
+            b_resident_nt = nt;
+          } else {
+            bb = (nb == 2) ? (int)(b_count & 1) : 0;
+          }
+          if (load_b) {
+            // a multi-chunk layer reuses the buffer while older MMAs may still read it: wait for their
+            // commit; a single-chunk layer reloads only across items (previous MMAs completed: bar_acc)
+            const uint32_t b_loads = bb ? b_loads1 : b_loads0;
+            if (p.n_chunks > 1 && b_loads > 0) mbar_wait(bar_b_free + 8 * bb, (b_loads - 1) & 1);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + c) * b_bytes;
+            mbar_expect_tx(bar_b_full + 8 * bb, b_bytes);
+            uint32_t off = 0;
+            while (off < b_bytes) {
+              const uint32_t n = min(b_bytes - off, 32768u);
+              bulk_g2s(B_addr + bb * b_bytes + off, src + off, n, bar_b_full + 8 * bb);
+              off += n;
+            }
+          }
+          for (int g = 0; g < tiles; ++g) {
+            const int ab = (na == 2) ? (int)(a_count & 1) : 0;
+            mbar_wait(bar_a_full + 8 * ab, (ab ? a_fills1 : a_fills0) & 1);
+            if (load_b && g == 0) mbar_wait(bar_b_full + 8 * bb, (bb ? b_loads1 : b_loads0) & 1);
+            tc_fence_after();
+            const uint64_t adesc0 = make_desc(A_addr + ab * a_bytes, (uint32_t)Rp * 16, 128);
+            const uint64_t bdesc0 = make_desc(B_addr + bb * b_bytes, (uint32_t)N * 16, 128);
+            const uint32_t alo0 = (uint32_t)adesc0, blo0 = (uint32_t)bdesc0;
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint32_t d_tmem = tmem_base + (uint32_t)((g * MB + mb) * N);
+              for (int tap = 0; tap < K; ++tap) {
+                uint32_t al = alo0 + (uint32_t)(mb * 128 + tap * dil);                 // 16 B units
+                uint32_t bl = blo0 + (uint32_t)tap * (uint32_t)(KC * N * 4 / 16);
+                for (int kk = 0; kk < KC / 8; ++kk) {
+                  const uint64_t a_hi = desc_with_lo(adesc0, al), a_lo = desc_with_lo(adesc0, al + a_lo_delta);
+                  const uint64_t b_hi = desc_with_lo(bdesc0, bl), b_lo = desc_with_lo(bdesc0, bl + b_lo_delta);
+                  const uint32_t first = (c == 0 && tap == 0 && kk == 0) ? 0u : 1u;
+                  tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
+                  tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                  tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                  al += 2u * (uint32_t)Rp;
+                  bl += 2u * (uint32_t)N;
+                }
+              }
+            }
+            tc_commit(bar_a_free + 8 * ab);
+            if (g == tiles - 1 && p.n_chunks > 1) tc_commit(bar_b_free + 8 * bb);
+            if (ab) a_fills1 += 1; else a_fills0 += 1;
+            a_count += 1;
+          }
+          if (load_b) { if (bb) b_loads1 += 1; else b_loads0 += 1; }
+          if (p.n_chunks > 1) b_count += 1;
+        }
+        tc_commit(bar_acc);
+      }
+      __syncwarp();   // lanes 1..31 park here (no issue slots) while lane 0 drives the tensor pipe
+    } else {
+      // =========================== staging warps ===========================
+      const int t_hi = a.in_mask ? (int)(len < T ? len : T) : T;
+      const float* in_b = a.in + (long long)b * a.in_bs;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        const int c0 = c * KC;
+        const bool fast = full16 && (a.Cin - c0) >= KC;
+        for (int g = 0; g < tiles; ++g) {
+          const int ab = (na == 2) ? (int)(a_count & 1) : 0;
+          const uint32_t a_uses = ab ? a_uses1 : a_uses0;
           uint8_t* Ah = A0 + (size_t)ab * a_bytes;
           const int t_in0 = t_group0 + g * MT - a.pad_left;
           bool waited = (a_uses == 0);
-          for (int idx = tid; idx < Rp * nb16; idx += THREADS) {
-            const int q16 = idx / Rp, r = idx - q16 * Rp;
+          int q16 = 0, r = tid;
+          while (r >= Rp) { r -= Rp; ++q16; }
+          while (q16 < nb16) {
             const int t = t_in0 + r;
             const bool rok = (r < R) && (t >= 0) && (t < t_hi);
             const int ci0 = c0 + q16 * 16;
             const float* src = in_b + (long long)ci0 * a.in_cs + t;
             float v[16];
+            if (fast) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              v[e] = 0.f;
-              if (rok && (ci0 + e) < a.Cin && (q16 * 16 + e) < KC) v[e] = __ldg(src + (long long)e * a.in_cs);
+              for (int e = 0; e < 16; ++e) v[e] = rok ? __ldg(src + (long long)e * a.in_cs) : 0.f;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                v[e] = 0.f;
+                if (rok && (ci0 + e) < a.Cin && (q16 * 16 + e) < KC) v[e] = __ldg(src + (long long)e * a.in_cs);
+              }
             }
-            if (!waited) {  // the MMAs that read this buffer last must be done before we overwrite it
+            if (!waited) {  // the MMAs that last read this buffer must be done before it is overwritten
               mbar_wait(bar_a_free + 8 * ab, (a_uses - 1) & 1);
               waited = true;
             }
 #pragma unroll
             for (int cg = 0; cg < 4; ++cg) {
-              if (q16 * 16 + cg * 4 < KC) {
+              if (fast || q16 * 16 + cg * 4 < KC) {
                 float4 hi, lo;
                 float x0 = v[cg * 4 + 0], x1 = v[cg * 4 + 1], x2 = v[cg * 4 + 2], x3 = v[cg * 4 + 3];
                 if (a.pre_act) {
@@ -233,45 +409,19 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
                 *reinterpret_cast<float4*>(Ah + a_half + o) = lo;
               }
             }
+            r += STAGERS;
+            while (r >= Rp) { r -= Rp; ++q16; }
           }
           if (!waited) mbar_wait(bar_a_free + 8 * ab, (a_uses - 1) & 1);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_a_full + 8 * ab);
+          if (ab) a_uses1 += 1; else a_uses0 += 1;
+          a_count += 1;
         }
-        fence_async_smem();
-        __syncthreads();
-        // ---------------- issue the MMAs of (tile g, chunk c)
-        if (tid == 0) {
-          if (load_b && g == 0) mbar_wait(bar_b_full + 8 * bb, b_loads & 1);
-          tc_fence_after();
-          const uint64_t adesc0 = make_desc(A_addr + ab * a_bytes, (uint32_t)Rp * 16, 128);
-          const uint64_t bdesc0 = make_desc(B_addr + bb * b_bytes, (uint32_t)N * 16, 128);
-          for (int mb = 0; mb < MB; ++mb) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)((g * MB + mb) * N);
-            for (int tap = 0; tap < K; ++tap) {
-              const uint32_t a_row_off = (uint32_t)(mb * 128 + tap * dil);           // in 16 B units
-              const uint32_t b_tap_off = (uint32_t)tap * (uint32_t)(KC * N * 4 / 16);
-              for (int kk = 0; kk < KC / 8; ++kk) {
-                const uint32_t a_off = a_row_off + (uint32_t)(2 * kk) * (uint32_t)Rp;
-                const uint32_t b_off = b_tap_off + (uint32_t)(2 * kk) * (uint32_t)N;
-                const uint64_t a_hi = adesc0 + a_off, a_lo = adesc0 + a_off + (a_half >> 4);
-                const uint64_t b_hi = bdesc0 + b_off, b_lo = bdesc0 + b_off + (b_half >> 4);
-                const uint32_t first = (c == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-                tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
-                tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-                tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
-              }
-            }
-          }
-          tc_commit(bar_a_free + 8 * ab);
-          if (g == tiles - 1 && p.n_chunks > 1) tc_commit(bar_b_free + 8 * bb);
-        }
-        if (ab) a_uses1 += 1; else a_uses0 += 1;
-        a_count += 1;
       }
-      if (load_b) { if (bb) b_loads1 += 1; else b_loads0 += 1; }
-      if (p.n_chunks > 1) b_count += 1;
     }
-    // ---------------- accumulators complete -> fused epilogue
-    if (tid == 0) tc_commit(bar_acc);
+    // ---------------- accumulators complete -> fused epilogue (all warps)
     mbar_wait(bar_acc, acc_count & 1);
     acc_count += 1;
     tc_fence_after();
@@ -287,37 +437,18 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
           for (int cc = 0; cc < ncol; cc += 16) {
             float v[16];
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + col0 + cc, v);
-            const int co0 = nt * N + part * ncol + cc;
-            if (t >= T) {
-              // nothing to store for rows past the end (the warp still ran the aligned tcgen05.ld)
-            } else if (a.ep.mode == EPI_GATE) {
+            const int nl = part * ncol + cc;
+            const float4* a4 = reinterpret_cast<const float4*>(av + nl);
 #pragma unroll
-              for (int i = 0; i < 16; i += 2) {
-                const int co = co0 + i;
-                if (co < a.Cout) {
-                  float ba, bbias;
-                  gate_terms(a, b, co, ba, bbias);
-                  gate_store(a, b, co, t, v[i] + ba, v[i + 1] + bbias);
-                }
-              }
-            } else {
-              EpiLoad l[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (co0 + i < a.Cout) l[i] = epilogue_load(a, b, co0 + i, t);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int co = co0 + i;
-                if (co < a.Cout) epilogue_finish(a, b, co, t, v[i] + channel_term(a, b, co), msk, l[i]);
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float4 x = a4[i];
+              v[4 * i + 0] += x.x; v[4 * i + 1] += x.y; v[4 * i + 2] += x.z; v[4 * i + 3] += x.w;
             }
+            if (t < T && nt * N + nl < a.Cout) tc_epilogue_slice(a, b, t, nt * N + nl, v, msk);
           }
         }
       }
     }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
   }
   __syncthreads();
   if (warp == 0) {
@@ -358,7 +489,7 @@ __global__ void pack_conv_tc_kernel(const float* __restrict__ src, float* __rest
 size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_abuf, int n_bbuf) {
   const int R = 128 * MB + (K - 1) * dil;
   const int Rp = (R + 7) & ~7;
-  return 128 + (size_t)n_abuf * (2 * (size_t)KC * Rp * 4) + (size_t)n_bbuf * (2 * (size_t)K * KC * N * 4);
+  return 128 + 2048 + (size_t)n_abuf * (2 * (size_t)KC * Rp * 4) + (size_t)n_bbuf * (2 * (size_t)K * KC * N * 4);
 }
 
 // Chooses the tiling.  mode 0 ("small"): <= 110 KB shared memory, 256 TMEM columns, 256 threads, two CTAs per
@@ -382,7 +513,7 @@ bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
     for (int na = 2; na >= 1; --na)
       for (int MB = 2; MB >= 1; --MB) {
         if (MB * N > 256) continue;
-        if (tc_conv_smem_bytes(K, dil, N, cin8, MB, na, 1) <= 110 * 1024) {
+        if (tc_conv_smem_bytes(K, dil, N, cin8, MB, na, 1) <= 108 * 1024) {
           fill(0, N, 1, cin8, MB, na, 1);
           return true;
         }
@@ -398,7 +529,7 @@ bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
       for (int nch = 1; nch <= cin8 / 8; ++nch) {
         const int KC = ((cin8 + nch - 1) / nch + 7) / 8 * 8;
         const int nb = (cin8 + KC - 1) / KC == 1 ? 1 : 2;
-        if (tc_conv_smem_bytes(K, dil, N, KC, MB, 2, nb) <= 220 * 1024) {
+        if (tc_conv_smem_bytes(K, dil, N, KC, MB, 2, nb) <= 216 * 1024) {
           fill(1, N, n_tiles, KC, MB, 2, nb);
           return true;
         }
