@@ -57,6 +57,7 @@ struct ConvT {
   float* w = nullptr;
   float* b = nullptr;
   int Cin = 0, Cout = 0, CoutPad = 0, k = 0, u = 1, ntaps = 2, pad = 0;
+  Conv as_conv;  // polyphase form as a Conv1d with Cout*u channels (tensor-core path)
 };
 struct Ln {
   float* g = nullptr;
@@ -557,6 +558,14 @@ int wetts_vits_finalize(wetts_vits_t h) {
       int* dmap;
       if (h->upload_ints(idm, &dmap) || h->dalloc(&t.b, (size_t)t.CoutPad)) return 1;
       launch_gather_vec(b->d, t.b, dmap, t.CoutPad, 0);
+      {
+        Raw eq;
+        eq.dims = {(int64_t)t.Cout * t.u, (int64_t)t.Cin, (int64_t)t.ntaps};
+        float* eqb;
+        if (h->dalloc(&eq.d, eq.numel()) || h->dalloc(&eqb, (size_t)t.Cout * t.u)) return 1;
+        launch_convT_as_conv(w.d, b->d, eq.d, eqb, t.Cin, t.Cout, t.k, t.u, 0);
+        if (h->pack_conv_from(eq, eqb, {}, {}, &t.as_conv, 1)) return 1;
+      }
       ch = t.Cout;
       for (int j = 0; j < c.n_resblock_kernels; ++j) {
         wetts_vits_s::ResBlock rb;
@@ -934,7 +943,19 @@ int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_len
     ConvTArgs ta;
     ta.in = w.x[cur]; ta.w = up.w; ta.bias = up.b; ta.out = w.xu; ta.B = B; ta.Cin = up.Cin; ta.Cout = up.Cout;
     ta.CoutPad = up.CoutPad; ta.T = len; ta.u = up.u; ta.ntaps = up.ntaps; ta.pad = up.pad; ta.pre_slope = 0.1f;
-    launch_conv_transpose1d(ta, s);
+    if (up.as_conv.wtc && tensor_cores_enabled() && len + 1 >= 64) {
+      // polyphase form on the tensor pipe: a 2-tap conv over the input frames with Cout*u packed channels
+      ConvArgs ca = conv_args(up.as_conv, w.x[cur], (long long)up.Cin * len, len, B, len, 1);
+      ca.T = len + up.ntaps - 1;       // frames q = 0 .. len + ntaps - 2 reach output samples
+      ca.in_T = len;                   // valid input frames
+      ca.pad_left = up.ntaps - 1;
+      ca.pre_act = 1; ca.pre_slope = 0.1f;
+      ca.ep.mode = EPI_CONVT; ca.ep.out = w.xu; ca.ep.out_bs = (long long)up.Cout * len * up.u;
+      ca.ep.up_u = up.u; ca.ep.up_pad = up.pad; ca.ep.out_T = (long long)len * up.u;
+      launch_conv1d(ca, s);
+    } else {
+      launch_conv_transpose1d(ta, s);
+    }
     len *= up.u;
     const int ch = up.Cout;
     const long long bs = (long long)ch * len;

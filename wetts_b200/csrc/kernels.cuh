@@ -13,6 +13,7 @@ enum EpiMode : int {
   EPI_GATE = 3,      // paired channels -> tanh(a+ga)*sigmoid(b+gb)   (modules.py:76-77)
   EPI_RES_SKIP = 4,  // co<H: x=(x+v)*mask ; co>=H: skip(+)=v         (modules.py:81-86)
   EPI_COUPLING = 5,  // z1 = (z1 - v*mask)*mask                       (flows.py:510)
+  EPI_CONVT = 6,     // polyphase ConvTranspose1d scatter (tensor-core path only)
 };
 
 struct ConvEpilogue {
@@ -34,6 +35,8 @@ struct ConvEpilogue {
   int last = 0;              // last WN layer: all Cout channels go to skip
   int z_c0 = 0;              // EPI_COUPLING: target channel = z_c0 + co*z_cstep in `out`
   int z_cstep = 1;
+  int up_u = 1, up_pad = 0;  // EPI_CONVT: stride and padding of the transposed conv
+  long long out_T = 0;       // EPI_CONVT: output samples per channel
 };
 
 // tiling of the tcgen05 implicit-GEMM path (tc_conv_kernel.cu), fixed per conv at load time
@@ -52,6 +55,7 @@ struct ConvArgs {
   const float* w = nullptr;   // packed [Cin][K][CoutPad]
   const float* bias = nullptr;  // packed [CoutPad] or nullptr
   int B = 0, Cin = 0, Cout = 0, CoutPad = 0, T = 0, K = 1, dil = 1, pad_left = 0;
+  int in_T = 0;               // valid input length when it differs from T (0: same as T); tensor-core path only
   int pre_act = 0;            // 1: leaky_relu(pre_slope) applied to the input
   float pre_slope = 0.1f;
   const long long* lengths = nullptr;  // int64[B] or nullptr
@@ -96,6 +100,8 @@ void launch_pack_conv(const float* src, float* dst, const int* co_map, const int
 // dst[ci][tap][co][r] = src[ci][co][r + tap*u]  (src [Cin][Cout][k]); co >= Cout -> 0
 void launch_pack_convT(const float* src, float* dst, int Cin, int Cout, int CoutPad, int k, int u, cudaStream_t s);
 void launch_gather_vec(const float* src, float* dst, const int* map, int n, cudaStream_t s);
+void launch_convT_as_conv(const float* src, const float* bias, float* dst, float* bias_out, int Cin, int Cout, int k, int u,
+                          cudaStream_t s);
 
 // ---------------------------------------------------------------- elementwise / norm
 void launch_embed(const long long* ids, const long long* lengths, const float* table, float* out, int B, int Tx, int H,

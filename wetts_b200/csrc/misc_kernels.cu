@@ -57,6 +57,22 @@ __global__ void pack_convT_kernel(const float* __restrict__ src, float* __restri
   }
 }
 
+// ConvTranspose1d weight [Cin][Cout][k] -> equivalent Conv1d weight [Cout*u][Cin][ntaps] of the polyphase
+// form: W'[co*u + r][ci][k'] = W[ci][co][r + (ntaps-1-k')*u]; bias'[co*u + r] = bias[co]
+__global__ void convT_as_conv_kernel(const float* __restrict__ src, const float* __restrict__ bias,
+                                     float* __restrict__ dst, float* __restrict__ bias_out, int Cin, int Cout, int k, int u) {
+  const int ntaps = k / u;
+  const long long n = (long long)Cout * u * Cin * ntaps;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int kp = (int)(i % ntaps);
+    const int ci = (int)((i / ntaps) % Cin);
+    const int cp = (int)(i / ((long long)ntaps * Cin));
+    const int co = cp / u, r = cp - co * u;
+    dst[i] = src[((long long)ci * Cout + co) * k + r + (ntaps - 1 - kp) * u];
+    if (ci == 0 && kp == 0) bias_out[cp] = bias[co];
+  }
+}
+
 __global__ void gather_vec_kernel(const float* __restrict__ src, float* __restrict__ dst, const int* __restrict__ map,
                                   int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -567,6 +583,13 @@ void launch_pack_convT(const float* src, float* dst, int Cin, int Cout, int Cout
   const long long n = (long long)Cin * (k / u) * CoutPad * u;
   pack_convT_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, dst, Cin, Cout, CoutPad,
                                                                                              k, u);
+  count_launch();
+}
+void launch_convT_as_conv(const float* src, const float* bias, float* dst, float* bias_out, int Cin, int Cout, int k, int u,
+                          cudaStream_t s) {
+  const long long n = (long long)Cout * u * Cin * (k / u);
+  convT_as_conv_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256, 0, s>>>(src, bias, dst, bias_out, Cin,
+                                                                                               Cout, k, u);
   count_launch();
 }
 void launch_gather_vec(const float* src, float* dst, const int* map, int n, cudaStream_t s) {

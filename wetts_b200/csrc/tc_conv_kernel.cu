@@ -180,6 +180,21 @@ __device__ __forceinline__ void tc_epilogue_slice(const ConvArgs& a, int b, int 
       }
       break;
     }
+    case EPI_CONVT: {
+      // polyphase ConvTranspose1d: packed channel = co*u + r, row t = input frame q; output sample
+      // n = q*u + r - pad of channel co (consecutive r are consecutive samples: coalesced)
+      const int u = e.up_u;
+      const long long n0 = (long long)t * u - e.up_pad;
+      float* ob = e.out + (size_t)b * (size_t)e.out_bs;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int cp = co0 + i;
+        const int co = cp / u, r = cp - co * u;
+        const long long n = n0 + r;
+        if (i < nval && n >= 0 && n < e.out_T) ob[(size_t)co * (size_t)e.out_T + (size_t)n] = v[i];
+      }
+      break;
+    }
     case EPI_COUPLING: {
       float* zp = e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts;
       const long long step = (long long)e.z_cstep * (long long)Ts;
@@ -306,20 +321,28 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
           } else {
             bb = (nb == 2) ? (int)(b_count & 1) : 0;
           }
-          if (load_b) {
-            // a multi-chunk layer reuses the buffer while older MMAs may still read it: wait for their
-            // commit; a single-chunk layer reloads only across items (previous MMAs completed: bar_acc)
-            const uint32_t b_loads = bb ? b_loads1 : b_loads0;
-            if (p.n_chunks > 1 && b_loads > 0) mbar_wait(bar_b_free + 8 * bb, (b_loads - 1) & 1);
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + c) * b_bytes;
-            mbar_expect_tx(bar_b_full + 8 * bb, b_bytes);
+          // Weight tiles.  Single-chunk layers: one resident tile, reloaded only when the item's N tile
+          // changes (the previous item's MMAs are complete: bar_acc + the item barrier).  Multi-chunk
+          // layers: two buffers; chunk c+1 is requested as soon as the first tile of chunk c has been
+          // issued (its buffer was last read by chunk c-1, whose commit we wait for), so the bulk copy
+          // overlaps the remaining tiles of chunk c.
+          auto issue_b_load = [&](int chunk, int buf, uint32_t loads_before) {
+            if (p.n_chunks > 1 && loads_before > 0) mbar_wait(bar_b_free + 8 * buf, (loads_before - 1) & 1);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + chunk) * b_bytes;
+            mbar_expect_tx(bar_b_full + 8 * buf, b_bytes);
             uint32_t off = 0;
             while (off < b_bytes) {
               const uint32_t n = min(b_bytes - off, 32768u);
-              bulk_g2s(B_addr + bb * b_bytes + off, src + off, n, bar_b_full + 8 * bb);
+              bulk_g2s(B_addr + buf * b_bytes + off, src + off, n, bar_b_full + 8 * buf);
               off += n;
             }
+          };
+          bool prefetched = false;
+          if (p.n_chunks > 1) {
+            load_b = true;
+            if (c > 0 && nb == 2) prefetched = true;  // requested during the previous chunk
           }
+          if (load_b && !prefetched) issue_b_load(c, bb, bb ? b_loads1 : b_loads0);
           for (int g = 0; g < tiles; ++g) {
             const int ab = (na == 2) ? (int)(a_count & 1) : 0;
             mbar_wait(bar_a_full + 8 * ab, (ab ? a_fills1 : a_fills0) & 1);
@@ -349,6 +372,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
             if (g == tiles - 1 && p.n_chunks > 1) tc_commit(bar_b_free + 8 * bb);
             if (ab) a_fills1 += 1; else a_fills0 += 1;
             a_count += 1;
+            if (g == 0 && nb == 2 && c + 1 < p.n_chunks) {
+              // prefetch the next chunk's weights into the other buffer (loads counted when consumed)
+              const int ob = bb ^ 1;
+              issue_b_load(c + 1, ob, ob ? b_loads1 : b_loads0);
+            }
           }
           if (load_b) { if (bb) b_loads1 += 1; else b_loads0 += 1; }
           if (p.n_chunks > 1) b_count += 1;
@@ -358,7 +386,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
       __syncwarp();   // lanes 1..31 park here (no issue slots) while lane 0 drives the tensor pipe
     } else {
       // =========================== staging warps ===========================
-      const int t_hi = a.in_mask ? (int)(len < T ? len : T) : T;
+      const int Tin = a.in_T > 0 ? a.in_T : T;
+      const int t_hi = a.in_mask ? (int)(len < Tin ? len : Tin) : Tin;
       const float* in_b = a.in + (long long)b * a.in_bs;
       for (int c = 0; c < p.n_chunks; ++c) {
         const int c0 = c * KC;
@@ -513,7 +542,7 @@ bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
     for (int na = 2; na >= 1; --na)
       for (int MB = 2; MB >= 1; --MB) {
         if (MB * N > 256) continue;
-        if (tc_conv_smem_bytes(K, dil, N, cin8, MB, na, 1) <= 108 * 1024) {
+        if (tc_conv_smem_bytes(K, dil, N, cin8, MB, na, 1) <= 112 * 1024) {
           fill(0, N, 1, cin8, MB, na, 1);
           return true;
         }
