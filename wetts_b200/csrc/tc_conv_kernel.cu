@@ -94,6 +94,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
+// true in exactly one (converged) lane of the warp; keeps the surrounding control flow warp-uniform so
+// that descriptors and addresses stay in uniform registers (no per-MMA R2UR waterfall)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -310,8 +321,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
     tc_fence_after();
 
     if (warp == MMA_WARP) {
-      // =========================== tensor-pipe warp (one elected lane) ===========================
-      if (lane == 0) {
+      // ================= tensor-pipe warp: uniform control flow, one elected lane issues =================
+      {
         for (int c = 0; c < p.n_chunks; ++c) {
           int bb = 0;
           bool load_b = true;
@@ -329,13 +340,16 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
           auto issue_b_load = [&](int chunk, int buf, uint32_t loads_before) {
             if (p.n_chunks > 1 && loads_before > 0) mbar_wait(bar_b_free + 8 * buf, (loads_before - 1) & 1);
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + chunk) * b_bytes;
-            mbar_expect_tx(bar_b_full + 8 * buf, b_bytes);
-            uint32_t off = 0;
-            while (off < b_bytes) {
-              const uint32_t n = min(b_bytes - off, 32768u);
-              bulk_g2s(B_addr + buf * b_bytes + off, src + off, n, bar_b_full + 8 * buf);
-              off += n;
+            if (elect_one()) {
+              mbar_expect_tx(bar_b_full + 8 * buf, b_bytes);
+              uint32_t off = 0;
+              while (off < b_bytes) {
+                const uint32_t n = min(b_bytes - off, 32768u);
+                bulk_g2s(B_addr + buf * b_bytes + off, src + off, n, bar_b_full + 8 * buf);
+                off += n;
+              }
             }
+            __syncwarp();
           };
           bool prefetched = false;
           if (p.n_chunks > 1) {
@@ -360,16 +374,21 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
                   const uint64_t a_hi = desc_with_lo(adesc0, al), a_lo = desc_with_lo(adesc0, al + a_lo_delta);
                   const uint64_t b_hi = desc_with_lo(bdesc0, bl), b_lo = desc_with_lo(bdesc0, bl + b_lo_delta);
                   const uint32_t first = (c == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-                  tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
-                  tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-                  tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                  if (elect_one()) {
+                    tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
+                    tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+                    tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+                  }
                   al += 2u * (uint32_t)Rp;
                   bl += 2u * (uint32_t)N;
                 }
               }
             }
-            tc_commit(bar_a_free + 8 * ab);
-            if (g == tiles - 1 && p.n_chunks > 1) tc_commit(bar_b_free + 8 * bb);
+            if (elect_one()) {
+              tc_commit(bar_a_free + 8 * ab);
+              if (g == tiles - 1 && p.n_chunks > 1) tc_commit(bar_b_free + 8 * bb);
+            }
+            __syncwarp();
             if (ab) a_fills1 += 1; else a_fills0 += 1;
             a_count += 1;
             if (g == 0 && nb == 2 && c + 1 < p.n_chunks) {
@@ -381,9 +400,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
           if (load_b) { if (bb) b_loads1 += 1; else b_loads0 += 1; }
           if (p.n_chunks > 1) b_count += 1;
         }
-        tc_commit(bar_acc);
+        if (elect_one()) tc_commit(bar_acc);
+        __syncwarp();
       }
-      __syncwarp();   // lanes 1..31 park here (no issue slots) while lane 0 drives the tensor pipe
     } else {
       // =========================== staging warps ===========================
       const int Tin = a.in_T > 0 ? a.in_T : T;
@@ -398,22 +417,30 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
           uint8_t* Ah = A0 + (size_t)ab * a_bytes;
           const int t_in0 = t_group0 + g * MT - a.pad_left;
           bool waited = (a_uses == 0);
+          // two (row, 16-channel) items per round: 32 independent global loads per thread in flight
           int q16 = 0, r = tid;
           while (r >= Rp) { r -= Rp; ++q16; }
           while (q16 < nb16) {
-            const int t = t_in0 + r;
-            const bool rok = (r < R) && (t >= 0) && (t < t_hi);
-            const int ci0 = c0 + q16 * 16;
-            const float* src = in_b + (long long)ci0 * a.in_cs + t;
-            float v[16];
-            if (fast) {
+            int q16b = q16, rb = r + STAGERS;
+            while (rb >= Rp) { rb -= Rp; ++q16b; }
+            const bool has_b = q16b < nb16;
+            float v[2][16];
+            int rr[2] = {r, rb}, qq[2] = {q16, q16b};
 #pragma unroll
-              for (int e = 0; e < 16; ++e) v[e] = rok ? __ldg(src + (long long)e * a.in_cs) : 0.f;
-            } else {
+            for (int u2 = 0; u2 < 2; ++u2) {
+              const int t = t_in0 + rr[u2];
+              const bool rok = (u2 == 0 || has_b) && (rr[u2] < R) && (t >= 0) && (t < t_hi);
+              const int ci0 = c0 + qq[u2] * 16;
+              const float* src = in_b + (long long)ci0 * a.in_cs + t;
+              if (fast) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                v[e] = 0.f;
-                if (rok && (ci0 + e) < a.Cin && (q16 * 16 + e) < KC) v[e] = __ldg(src + (long long)e * a.in_cs);
+                for (int e = 0; e < 16; ++e) v[u2][e] = rok ? __ldg(src + (long long)e * a.in_cs) : 0.f;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  v[u2][e] = 0.f;
+                  if (rok && (ci0 + e) < a.Cin && (qq[u2] * 16 + e) < KC) v[u2][e] = __ldg(src + (long long)e * a.in_cs);
+                }
               }
             }
             if (!waited) {  // the MMAs that last read this buffer must be done before it is overwritten
@@ -421,24 +448,29 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
               waited = true;
             }
 #pragma unroll
-            for (int cg = 0; cg < 4; ++cg) {
-              if (fast || q16 * 16 + cg * 4 < KC) {
-                float4 hi, lo;
-                float x0 = v[cg * 4 + 0], x1 = v[cg * 4 + 1], x2 = v[cg * 4 + 2], x3 = v[cg * 4 + 3];
-                if (a.pre_act) {
-                  x0 = x0 > 0.f ? x0 : x0 * a.pre_slope; x1 = x1 > 0.f ? x1 : x1 * a.pre_slope;
-                  x2 = x2 > 0.f ? x2 : x2 * a.pre_slope; x3 = x3 > 0.f ? x3 : x3 * a.pre_slope;
+            for (int u2 = 0; u2 < 2; ++u2) {
+              if (u2 == 1 && !has_b) break;
+#pragma unroll
+              for (int cg = 0; cg < 4; ++cg) {
+                if (fast || qq[u2] * 16 + cg * 4 < KC) {
+                  float4 hi, lo;
+                  float x0 = v[u2][cg * 4 + 0], x1 = v[u2][cg * 4 + 1], x2 = v[u2][cg * 4 + 2], x3 = v[u2][cg * 4 + 3];
+                  if (a.pre_act) {
+                    x0 = x0 > 0.f ? x0 : x0 * a.pre_slope; x1 = x1 > 0.f ? x1 : x1 * a.pre_slope;
+                    x2 = x2 > 0.f ? x2 : x2 * a.pre_slope; x3 = x3 > 0.f ? x3 : x3 * a.pre_slope;
+                  }
+                  hi.x = tf32_rna(x0); lo.x = tf32_rna(x0 - hi.x);
+                  hi.y = tf32_rna(x1); lo.y = tf32_rna(x1 - hi.y);
+                  hi.z = tf32_rna(x2); lo.z = tf32_rna(x2 - hi.z);
+                  hi.w = tf32_rna(x3); lo.w = tf32_rna(x3 - hi.w);
+                  const size_t o = ((size_t)(qq[u2] * 4 + cg) * Rp + rr[u2]) * 16;
+                  *reinterpret_cast<float4*>(Ah + o) = hi;
+                  *reinterpret_cast<float4*>(Ah + a_half + o) = lo;
                 }
-                hi.x = tf32_rna(x0); lo.x = tf32_rna(x0 - hi.x);
-                hi.y = tf32_rna(x1); lo.y = tf32_rna(x1 - hi.y);
-                hi.z = tf32_rna(x2); lo.z = tf32_rna(x2 - hi.z);
-                hi.w = tf32_rna(x3); lo.w = tf32_rna(x3 - hi.w);
-                const size_t o = ((size_t)(q16 * 4 + cg) * Rp + r) * 16;
-                *reinterpret_cast<float4*>(Ah + o) = hi;
-                *reinterpret_cast<float4*>(Ah + a_half + o) = lo;
               }
             }
-            r += STAGERS;
+            r = rb + STAGERS;
+            q16 = q16b;
             while (r >= Rp) { r -= Rp; ++q16; }
           }
           if (!waited) mbar_wait(bar_a_free + 8 * ab, (a_uses - 1) & 1);
