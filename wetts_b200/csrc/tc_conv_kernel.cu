@@ -67,6 +67,21 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The three 3xTF32 MMAs of one (tap, k-step) issued by one elected lane WITHOUT a C++ branch: the
+// election and the predication live inside the asm block, so the surrounding loop is straight-line
+// warp-uniform code (no BSSY/BSYNC reconvergence, operands stay uniform).
+__device__ __forceinline__ void tc_mma_tf32_x3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
+                                               uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %6, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, pa;\n\t"    // lo * hi (small terms first)
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, 1;\n\t"     // hi * lo
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %5, 1;\n\t}"    // hi * hi
+      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -374,11 +389,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
                   const uint64_t a_hi = desc_with_lo(adesc0, al), a_lo = desc_with_lo(adesc0, al + a_lo_delta);
                   const uint64_t b_hi = desc_with_lo(bdesc0, bl), b_lo = desc_with_lo(bdesc0, bl + b_lo_delta);
                   const uint32_t first = (c == 0 && tap == 0 && kk == 0) ? 0u : 1u;
-                  if (elect_one()) {
-                    tc_mma_tf32(d_tmem, a_lo, b_hi, idesc, first);   // small terms first
-                    tc_mma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-                    tc_mma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
-                  }
+                  tc_mma_tf32_x3(d_tmem, a_hi, a_lo, b_hi, b_lo, idesc, first);
                   al += 2u * (uint32_t)Rp;
                   bl += 2u * (uint32_t)N;
                 }
