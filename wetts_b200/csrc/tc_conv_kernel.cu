@@ -19,6 +19,7 @@
 //   buffer reuse and accumulator completion; one persistent CTA per SM loops over work items
 //   and keeps the weight tile resident when it can.
 #include <cstdint>
+#include <cstdio>
 
 #include "epilogue.cuh"
 #include "kernels.cuh"
@@ -32,8 +33,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// Bounded spin: a pipeline bug must fail fast (trap + message) instead of hanging the GPU.
+__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
+  printf("wetts_b200: mbarrier wait timed out (smem 0x%x, parity %u, block %d, thread %d)\n", bar, parity,
+         (int)blockIdx.x, (int)threadIdx.x);
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
+  uint32_t spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -42,6 +50,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+    if (!done && ++spins > (1u << 24)) mbar_timeout(bar, parity);
   } while (!done);
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -246,8 +255,13 @@ __device__ __forceinline__ void tc_epilogue_slice(const ConvArgs& a, int b, int 
 // THREADS = 256 runs 2 CTAs/SM (256 TMEM columns each), THREADS = 512 one CTA/SM (512 columns).
 template <int THREADS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcConvArgs p) {
-  constexpr int STAGERS = THREADS - 32;   // threads that stage activations
-  constexpr int MMA_WARP = THREADS / 32 - 1;
+  // The issue loop of tcgen05.mma is software-bound (~115 cycles per MMA measured with clock64 timers:
+  // descriptor arithmetic + R2UR moves on one warp), and with N = 32..64 there are 36-84 MMAs per tile,
+  // so NI warps issue, each owning the tiles g with g % NI == its index (an accumulator is therefore
+  // always fed, in order, by the same warp).
+  constexpr int NI = 1;   // 2 deadlocks on hardware (an issuer commit never lands); kept parametric
+  constexpr int STAGERS = THREADS - 32 * NI;   // threads that stage activations
+  constexpr int FIRST_MMA_WARP = THREADS / 32 - NI;
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& a = p.c;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -281,7 +295,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int i = 0; i < 7; ++i) mbar_init(smem_u32(&bars[i]), 1);
+    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);   // a_free[2], b_full[2]
+    mbar_init(bar_b_free, NI);                                       // every issuer commits per chunk
+    mbar_init(bar_b_free + 8, NI);
+    mbar_init(bar_acc, NI);                                          // every issuer commits per item
     mbar_init(bar_a_full, STAGERS / 32);
     mbar_init(bar_a_full + 8, STAGERS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -335,8 +352,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
     __syncthreads();
     tc_fence_after();
 
-    if (warp == MMA_WARP) {
-      // ================= tensor-pipe warp: uniform control flow, one elected lane issues =================
+    if (warp >= FIRST_MMA_WARP) {
+      // ============ tensor-pipe warps: uniform control flow, one elected lane per warp issues ============
+      const int iw = warp - FIRST_MMA_WARP;
       {
         for (int c = 0; c < p.n_chunks; ++c) {
           int bb = 0;
@@ -353,9 +371,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
           // issued (its buffer was last read by chunk c-1, whose commit we wait for), so the bulk copy
           // overlaps the remaining tiles of chunk c.
           auto issue_b_load = [&](int chunk, int buf, uint32_t loads_before) {
-            if (p.n_chunks > 1 && loads_before > 0) mbar_wait(bar_b_free + 8 * buf, (loads_before - 1) & 1);
+            if (iw == 0 && p.n_chunks > 1 && loads_before > 0) mbar_wait(bar_b_free + 8 * buf, (loads_before - 1) & 1);
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + chunk) * b_bytes;
-            if (elect_one()) {
+            if (iw == 0 && elect_one()) {
               mbar_expect_tx(bar_b_full + 8 * buf, b_bytes);
               uint32_t off = 0;
               while (off < b_bytes) {
@@ -372,10 +390,17 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
             if (c > 0 && nb == 2) prefetched = true;  // requested during the previous chunk
           }
           if (load_b && !prefetched) issue_b_load(c, bb, bb ? b_loads1 : b_loads0);
+          bool b_ready = !load_b;
           for (int g = 0; g < tiles; ++g) {
             const int ab = (na == 2) ? (int)(a_count & 1) : 0;
+            if (g % NI != iw) {   // another issuer's tile: only keep the pipeline counters in step
+              if (ab) a_fills1 += 1; else a_fills0 += 1;
+              a_count += 1;
+              if (g == 0 && nb == 2 && c + 1 < p.n_chunks) { const int ob = bb ^ 1; issue_b_load(c + 1, ob, ob ? b_loads1 : b_loads0); }
+              continue;
+            }
             mbar_wait(bar_a_full + 8 * ab, (ab ? a_fills1 : a_fills0) & 1);
-            if (load_b && g == 0) mbar_wait(bar_b_full + 8 * bb, (bb ? b_loads1 : b_loads0) & 1);
+            if (!b_ready) { mbar_wait(bar_b_full + 8 * bb, (bb ? b_loads1 : b_loads0) & 1); b_ready = true; }
             tc_fence_after();
             const uint64_t adesc0 = make_desc(A_addr + ab * a_bytes, (uint32_t)Rp * 16, 128);
             const uint64_t bdesc0 = make_desc(B_addr + bb * b_bytes, (uint32_t)N * 16, 128);
@@ -395,10 +420,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
                 }
               }
             }
-            if (elect_one()) {
-              tc_commit(bar_a_free + 8 * ab);
-              if (g == tiles - 1 && p.n_chunks > 1) tc_commit(bar_b_free + 8 * bb);
-            }
+            if (elect_one()) tc_commit(bar_a_free + 8 * ab);
             __syncwarp();
             if (ab) a_fills1 += 1; else a_fills0 += 1;
             a_count += 1;
@@ -408,6 +430,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
               issue_b_load(c + 1, ob, ob ? b_loads1 : b_loads0);
             }
           }
+          // every issuer reports "my MMAs that read this weight buffer are done" (also when it had no tile)
+          if (p.n_chunks > 1 && elect_one()) tc_commit(bar_b_free + 8 * bb);
+          __syncwarp();
           if (load_b) { if (bb) b_loads1 += 1; else b_loads0 += 1; }
           if (p.n_chunks > 1) b_count += 1;
         }
