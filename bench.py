@@ -194,6 +194,7 @@ def run_ours(args):
         B = args.batch
     from wetts_b200 import _lib
     _lib.check(_lib.load().wetts_set_option(b"tensor_cores", int(args.tensor_cores)))
+    _lib.check(_lib.load().wetts_set_option(b"fused_resblock", int(args.fused_resblock)))
     hps = builtin_config(cfg_name)
     sd = synth.make_state_dict(hps.model, n_vocab, n_spk, seed=hps.train.seed)
     net = wetts_b200.build_model(hps, n_vocab, n_spk, sd, dev)
@@ -304,7 +305,8 @@ def run_ours(args):
             "metric": "audio-seconds/sec (VITS infer)", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "config": cfg_name, "tensor_cores": bool(args.tensor_cores), "batch_per_gpu": B, "phonemes": Tx,
+            "config": {"workload": args.workload, "config": cfg_name, "tensor_cores": bool(args.tensor_cores),
+                       "fused_resblock": bool(args.fused_resblock), "batch_per_gpu": B, "phonemes": Tx,
                        "frames_max": Ty, "valid_frames_per_gpu": frames, "length_scale": ls,
                        "sampling_rate": sr, "scales": [ns, ls, nsw], "parallelism": f"batch-sharded x{world}",
                        "l2": "working set >> L2 (multi-GB activations per step); no explicit flush"},
@@ -342,6 +344,7 @@ def main():
     ap.add_argument("--profile-range", action="store_true",
                     help="wrap the timed region in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--tensor-cores", type=int, default=1, help="0: force the fp32 SIMT kernels")
+    ap.add_argument("--fused-resblock", type=int, default=1, help="0: one launch per generator conv (no fused MRF stage kernel)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -71,7 +71,10 @@ const char* wetts_last_error(void);
 const char* wetts_version(void);
 
 /* Process-wide options.  "tensor_cores": 1 (default) routes eligible convolutions through the
- * tcgen05 3xTF32 implicit-GEMM kernel (fp32-accurate), 0 forces the fp32 SIMT kernels. */
+ * tcgen05 3xTF32 implicit-GEMM kernel (fp32-accurate), 0 forces the fp32 SIMT kernels.
+ * "fused_resblock": 1 (default) runs each eligible HiFi-GAN stage (ResBlock2, 32 or 64 channels)
+ * as ONE fused MRF kernel (both convs of every resblock + the mean on chip), 0 keeps one launch
+ * per convolution.  Only effective with tensor_cores = 1. */
 int wetts_set_option(const char* name, int value);
 int wetts_get_option(const char* name, int* value);
 

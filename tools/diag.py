@@ -20,7 +20,9 @@ def main():
     from wetts_b200 import _lib
     tc = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     _lib.check(_lib.load().wetts_set_option(b"tensor_cores", tc))
-    print("tensor_cores =", tc, flush=True)
+    fused = int(os.environ.get("WETTS_FUSED_RB", "1"))
+    _lib.check(_lib.load().wetts_set_option(b"fused_resblock", fused))
+    print("tensor_cores =", tc, "fused_resblock =", fused, flush=True)
     cases = sys.argv[2:] if len(sys.argv) > 2 else CASES
     for name in cases:
         print("case", name, flush=True)

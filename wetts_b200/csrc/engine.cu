@@ -50,6 +50,7 @@ struct Conv {
   float* w = nullptr;    // SIMT layout [Cin][K][CoutPad]
   float* b = nullptr;
   float* wtc = nullptr;  // tcgen05 layout (tc_conv_kernel.cu), hi/lo tf32 split
+  const float* wraw = nullptr;  // folded source weight [Cout][Cin][K] (before any channel map)
   TcPlan tc;
   int Cin = 0, Cout = 0, CoutPad = 0, K = 1;
 };
@@ -139,6 +140,7 @@ struct wetts_vits_s {
     int k = 3;
   };
   std::vector<ResBlock> rbs;
+  std::vector<float*> fused_rb_w;  // per stage: packed weights of the fused MRF kernel (nullptr: per-layer path)
   float* conv_post_w = nullptr;
   int c_last = 0;
   float* emb_g = nullptr;
@@ -199,6 +201,7 @@ struct wetts_vits_s {
     c->CoutPad = round_cout(c->Cout);
     c->Cin = ci_map.empty() ? src_cin : (int)ci_map.size();
     c->K = K;
+    c->wraw = w.d;
     co_map.resize(c->CoutPad, -1);
     int *d_co = nullptr, *d_ci = nullptr;
     if (upload_ints(co_map, &d_co)) return 1;
@@ -389,6 +392,10 @@ int wetts_vits_upsample_factor(wetts_vits_t h) { return h ? h->U : 0; }
 
 int wetts_set_option(const char* name, int value) {
   if (!name) return fail("null option name");
+  if (!strcmp(name, "fused_resblock")) {
+    set_fused_resblock_enabled(value != 0);
+    return 0;
+  }
   if (!strcmp(name, "tensor_cores")) {
     set_tensor_cores_enabled(value != 0);
     return 0;
@@ -399,6 +406,10 @@ int wetts_get_option(const char* name, int* value) {
   if (!name || !value) return fail("null argument");
   if (!strcmp(name, "tensor_cores")) {
     *value = tensor_cores_enabled() ? 1 : 0;
+    return 0;
+  }
+  if (!strcmp(name, "fused_resblock")) {
+    *value = fused_resblock_enabled() ? 1 : 0;
     return 0;
   }
   return fail("unknown option '%s'", name);
@@ -587,6 +598,33 @@ int wetts_vits_finalize(wetts_vits_t h) {
           if (a.K != rb.k || a.Cin != ch) return fail("%s: shape does not match the config", rp.c_str());
         }
         h->rbs.push_back(rb);
+      }
+      // fused ResBlock2/MRF stage kernel (fused_rb_kernel.cuh) when the stage is eligible
+      h->fused_rb_w.push_back(nullptr);
+      if (c.resblock_type == 2 && c.n_resblock_kernels <= 3) {
+        const int nk = c.n_resblock_kernels;
+        int ks[3] = {0, 0, 0}, d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};
+        bool ok = true;
+        size_t floats = 0;
+        for (int j = 0; j < nk; ++j) {
+          const auto& rb = h->rbs[(size_t)i * nk + j];
+          ok = ok && rb.dil.size() == 2 && rb.c1.size() == 2 && rb.c1[0].b && rb.c1[1].b;
+          if (!ok) break;
+          ks[j] = rb.k; d1[j] = rb.dil[0]; d2[j] = rb.dil[1];
+          floats += 2 * fused_rb_conv_floats(ch, rb.k);
+        }
+        if (ok && fused_rb_supported(ch, nk, ks, d1, d2)) {
+          float* fw;
+          if (h->dalloc(&fw, floats)) return 1;
+          size_t off = 0;
+          for (int j = 0; j < nk; ++j)
+            for (int n = 0; n < 2; ++n) {
+              const Conv& cv = h->rbs[(size_t)i * nk + j].c1[n];
+              launch_fused_rb_pack(cv.wraw, fw + off, ch, cv.K, 0);
+              off += fused_rb_conv_floats(ch, cv.K);
+            }
+          h->fused_rb_w.back() = fw;
+        }
       }
     }
     h->c_last = ch;
@@ -960,6 +998,19 @@ int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_len
     const int ch = up.Cout;
     const long long bs = (long long)ch * len;
     float* acc = w.x[cur ^ 1];
+    if (h->fused_rb_w[i] && tensor_cores_enabled() && fused_resblock_enabled()) {
+      FusedRbArgs fa;
+      fa.in = w.xu; fa.out = acc; fa.w = h->fused_rb_w[i];
+      fa.B = B; fa.T = len; fa.nrb = nk; fa.slope = 0.1f; fa.div = (float)nk;
+      for (int j = 0; j < nk; ++j) {
+        const auto& rb = h->rbs[i * nk + j];
+        fa.k[j] = rb.k; fa.d1[j] = rb.dil[0]; fa.d2[j] = rb.dil[1];
+        fa.bias1[j] = rb.c1[0].b; fa.bias2[j] = rb.c1[1].b;
+      }
+      if (launch_fused_rb(ch, fa, s)) return fail("fused resblock launch failed");
+      cur ^= 1;
+      continue;
+    }
     for (int j = 0; j < nk; ++j) {
       const auto& rb = h->rbs[i * nk + j];
       const int nd = (int)rb.dil.size();

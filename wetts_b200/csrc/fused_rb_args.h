@@ -1,0 +1,70 @@
+// Arguments and packing rules of the fused ResBlock2/MRF stage kernel (fused_rb_kernel.cuh).
+// Plain C++ (no CUDA dependency): shared by the kernel, the engine and the host CTA emulator.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define WETTS_HD __host__ __device__
+#else
+#define WETTS_HD
+#endif
+
+namespace wetts {
+
+struct FusedRbArgs {
+  const float* in = nullptr;   // [B][C][T]
+  float* out = nullptr;        // [B][C][T]
+  const float* w = nullptr;    // packed chunk sequence of one item (fused_rb_pack_index)
+  const float* bias1[3] = {nullptr, nullptr, nullptr};
+  const float* bias2[3] = {nullptr, nullptr, nullptr};
+  int B = 0, T = 0, nrb = 0;
+  int k[3] = {0, 0, 0}, d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};
+  int Rp = 0;                  // rows of the activation buffer: >= 128 + 2*max_j H_j, multiple of 8
+  int nq = 0;                  // weight chunks per item = sum_j 2*k_j*(C/32)
+  int qoff[6] = {0, 0, 0, 0, 0, 0};  // first chunk (within the item) of conv 2*j + {0: conv1, 1: conv2}
+  float slope = 0.1f;
+  float div = 1.f;
+};
+
+constexpr int kFusedRbRing = 4;      // weight ring slots (power of two: slot and phase are bit fields of the chunk number)
+constexpr int kFusedRbAhead = 3;     // chunks requested ahead of the MMAs (ring - 1: the issuer runs one chunk ahead of the pipe)
+constexpr int kFusedRbUnits = 7;     // (row, 4-channel) staging units per thread  ->  R <= 224
+
+// floats of one weight chunk: [8 k-groups][hi|lo][N][4]  (hi and lo rows adjacent: one 2N-row operand)
+constexpr int fused_rb_chunk_floats(int C) { return 2 * 8 * C * 4; }
+inline size_t fused_rb_smem_bytes(int C, int Rp) {
+  return 128 + 2 * (size_t)C * Rp * 4 + (size_t)kFusedRbRing * fused_rb_chunk_floats(C) * 4;
+}
+// Derived launch fields (Rp, nq, qoff) from (nrb, k, d1, d2).
+inline void fused_rb_finalize_args(FusedRbArgs& a, int C) {
+  int Hmax = 0;
+  a.nq = 0;
+  for (int j = 0; j < a.nrb; ++j) {
+    const int H = (a.d1[j] + a.d2[j]) * (a.k[j] - 1) / 2;
+    if (H > Hmax) Hmax = H;
+    a.qoff[2 * j] = a.nq;
+    a.nq += a.k[j] * (C / 32);
+    a.qoff[2 * j + 1] = a.nq;
+    a.nq += a.k[j] * (C / 32);
+  }
+  a.Rp = (128 + 2 * Hmax + 7) & ~7;
+}
+
+// Packed weight element i of a conv [C][C][k] (chunk order: tap, 32-channel slice): returns the source
+// coordinates.  i indexes [tap][kh][kg][hl][n][e].
+struct FusedRbPackIdx { int tap, hl, co, ci; };
+WETTS_HD inline FusedRbPackIdx fused_rb_pack_index(long long i, int C) {
+  FusedRbPackIdx r;
+  const int e = (int)(i % 4); i /= 4;
+  const int n = (int)(i % C); i /= C;
+  r.hl = (int)(i % 2); i /= 2;
+  const int kg = (int)(i % 8); i /= 8;
+  const int kh = (int)(i % (C / 32)); i /= (C / 32);
+  r.tap = (int)i;
+  r.co = n;
+  r.ci = kh * 32 + kg * 4 + e;
+  return r;
+}
+
+}  // namespace wetts

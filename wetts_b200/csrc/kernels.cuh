@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fused_rb_args.h"
+
 namespace wetts {
 
 // ---------------------------------------------------------------- conv1d (fp32 SIMT)
@@ -77,6 +79,14 @@ void launch_pack_conv_tc(const float* src, float* dst, const int* co_map, const 
 void launch_conv1d_tc(const ConvArgs& a, cudaStream_t s);
 void set_tensor_cores_enabled(bool on);
 bool tensor_cores_enabled();
+
+// fused ResBlock2/MRF stage (fused_rb.cu): one launch per generator stage with C in {32, 64}
+bool fused_rb_supported(int C, int nrb, const int* k, const int* d1, const int* d2);
+size_t fused_rb_conv_floats(int C, int K);
+void launch_fused_rb_pack(const float* w_folded /*[C][C][K]*/, float* dst, int C, int K, cudaStream_t s);
+int launch_fused_rb(int C, FusedRbArgs a, cudaStream_t s);   // fills Rp / nq; returns 0 on success
+void set_fused_resblock_enabled(bool on);
+bool fused_resblock_enabled();
 
 struct ConvTArgs {
   const float* in = nullptr;  // [B][Cin][T]
