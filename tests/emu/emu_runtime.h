@@ -193,6 +193,12 @@ WETTS_DEVICE uint32_t smem_u32(const void* p) {
 WETTS_DEVICE void cta_sync() { emu::cta()->cta_bar->arrive_and_wait(); }
 WETTS_DEVICE void warp_sync() { emu::cta()->warp_bars[emu::g_tid >> 5]->arrive_and_wait(); }
 WETTS_DEVICE float ldg(const float* p) { return *p; }
+WETTS_DEVICE long long clock_now() { return 0; }
+WETTS_DEVICE void trap_now() { emu::die("kernel trap"); }
+WETTS_DEVICE float4 ldg4(const float* p) {
+  if ((uintptr_t)p & 15) emu::die("16 B load from a misaligned address");
+  return *reinterpret_cast<const float4*>(p);
+}
 
 WETTS_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
   std::lock_guard<std::mutex> g(emu::cta()->m);
@@ -279,6 +285,7 @@ WETTS_DEVICE void tc_mma_tf32_split2(uint32_t d_tmem, uint32_t d_tmem_small, uin
   emu::cta()->queue.push_back(o);
 }
 WETTS_DEVICE uint32_t warp_uniform(uint32_t v) { return v; }
+WETTS_DEVICE uint32_t uniform_bits(uint32_t v, int lo, int hi) { return v & (((hi >= 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)); }
 WETTS_DEVICE void tmem_ld16(uint32_t taddr, float* v) {
   const uint32_t lane_base = taddr >> 16, col = taddr & 0xFFFF;
   const int warp = emu::g_tid >> 5, lane = emu::g_tid & 31;
@@ -288,6 +295,8 @@ WETTS_DEVICE void tmem_ld16(uint32_t taddr, float* v) {
   std::lock_guard<std::mutex> g(emu::cta()->m);
   for (int i = 0; i < 16; ++i) v[i] = emu::cta()->tmem[lane_base + lane][col + i];
 }
+WETTS_DEVICE void tmem_ld16_nowait(uint32_t taddr, float* v) { tmem_ld16(taddr, v); }
+WETTS_DEVICE void tmem_ld_wait() {}
 WETTS_DEVICE void tmem_alloc(uint32_t slot_smem_addr, uint32_t cols) {
   if ((emu::g_tid & 31) != 0) return;
   if (cols < 32 || cols > 512 || (cols & (cols - 1))) emu::die("tcgen05.alloc: columns must be a power of two in [32, 512]");

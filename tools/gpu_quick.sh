@@ -11,3 +11,4 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-
     python bench.py --steps 1 --warmup 3 --no-cpu --profile-range > gpurun_out/ncu_bench.log 2>&1
 python tools/launches.py gpurun_out/launches.csv | head -20
 cat gpurun_out/bench.json
+WETTS_FUSED_RB_PROFILE=1 timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu > /dev/null 2> gpurun_out/prof.log; grep -A2 "fused_rb profile" gpurun_out/prof.log | tail -6

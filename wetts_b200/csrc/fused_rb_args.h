@@ -20,21 +20,25 @@ struct FusedRbArgs {
   const float* bias2[3] = {nullptr, nullptr, nullptr};
   int B = 0, T = 0, nrb = 0;
   int k[3] = {0, 0, 0}, d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};
-  int Rp = 0;                  // rows of the activation buffer: >= 128 + 2*max_j H_j, multiple of 8
+  int Rp = 0;                  // row pitch of a channel group in the activation buffer: >= 128 + 2*max_j Hp_j, odd
   int nq = 0;                  // weight chunks per item = sum_j 2*k_j*(C/32)
   int qoff[6] = {0, 0, 0, 0, 0, 0};  // first chunk (within the item) of conv 2*j + {0: conv1, 1: conv2}
+  uint32_t smem_off = 0;       // CTA-local shared-window offset of the dynamic shared memory base (see the kernel)
   float slope = 0.1f;
   float div = 1.f;
+  long long* prof = nullptr;   // profiling instantiation only: [grid][2][kFusedRbProfPhases] cycle sums
 };
+constexpr int kFusedRbProfPhases = 15;
 
 constexpr int kFusedRbRing = 4;      // weight ring slots (power of two: slot and phase are bit fields of the chunk number)
-constexpr int kFusedRbAhead = 3;     // chunks requested ahead of the MMAs (ring - 1: the issuer runs one chunk ahead of the pipe)
-constexpr int kFusedRbUnits = 7;     // (row, 4-channel) staging units per thread  ->  R <= 224
+constexpr int kFusedRbAhead = 4;     // chunks requested ahead of the MMAs (= ring: a slot is refilled the moment its chunk completes)
+constexpr int kFusedRbPitch = 225;   // rows per 4-channel group of the activation tile (odd; >= 128 + 2*48 halo rows)
+constexpr int kFusedRbUnits = 2;     // (4 rows x 4 channels) staging units per thread  ->  R <= 256 rows
 
 // floats of one weight chunk: [8 k-groups][hi|lo][N][4]  (hi and lo rows adjacent: one 2N-row operand)
 constexpr int fused_rb_chunk_floats(int C) { return 2 * 8 * C * 4; }
-inline size_t fused_rb_smem_bytes(int C, int Rp) {
-  return 128 + 2 * (size_t)C * Rp * 4 + (size_t)kFusedRbRing * fused_rb_chunk_floats(C) * 4;
+inline size_t fused_rb_smem_bytes(int C, int Rp = kFusedRbPitch) {
+  return 128 + (size_t)kFusedRbRing * fused_rb_chunk_floats(C) * 4 + 6 * (size_t)C * 4 + 2 * (size_t)C * Rp * 4;
 }
 // Derived launch fields (Rp, nq, qoff) from (nrb, k, d1, d2).
 inline void fused_rb_finalize_args(FusedRbArgs& a, int C) {
@@ -42,13 +46,15 @@ inline void fused_rb_finalize_args(FusedRbArgs& a, int C) {
   a.nq = 0;
   for (int j = 0; j < a.nrb; ++j) {
     const int H = (a.d1[j] + a.d2[j]) * (a.k[j] - 1) / 2;
-    if (H > Hmax) Hmax = H;
+    const int Hp = (H + 3) & ~3;
+    if (Hp > Hmax) Hmax = Hp;
     a.qoff[2 * j] = a.nq;
     a.nq += a.k[j] * (C / 32);
     a.qoff[2 * j + 1] = a.nq;
     a.nq += a.k[j] * (C / 32);
   }
-  a.Rp = (128 + 2 * Hmax + 7) & ~7;
+  a.Rp = kFusedRbPitch;   // compile-time pitch; fused_rb_supported() guarantees 128 + 2*Hmax <= pitch
+  (void)Hmax;
 }
 
 // Packed weight element i of a conv [C][C][k] (chunk order: tap, 32-channel slice): returns the source

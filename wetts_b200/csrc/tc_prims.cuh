@@ -30,6 +30,9 @@ WETTS_DEVICE uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_
 WETTS_DEVICE void cta_sync() { __syncthreads(); }
 WETTS_DEVICE void warp_sync() { __syncwarp(); }
 WETTS_DEVICE float ldg(const float* p) { return __ldg(p); }
+WETTS_DEVICE long long clock_now() { return clock64(); }
+WETTS_DEVICE void trap_now() { __trap(); }
+WETTS_DEVICE float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 WETTS_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -115,6 +118,16 @@ WETTS_DEVICE void tc_mma_tf32_split2(uint32_t d_tmem, uint32_t d_tmem_small, uin
 // Without this every tcgen05.mma operand takes an R2UR round trip (~90 cycles per MMA measured, see
 // tools/ubench/mma_ubench.cu) and small-N MMAs become issue-bound.
 WETTS_DEVICE uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+// Stronger form for small values: rebuild bits [lo, hi) from warp votes.  A vote result is a uniform predicate
+// (VOTEU -> UP), so the value is born in the uniform datapath; a shuffle result lives in a vector register and
+// ptxas may still convert it with one predicated R2UR per use.
+WETTS_DEVICE uint32_t uniform_bits(uint32_t v, int lo, int hi) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int b = lo; b < hi; ++b)
+    if (__any_sync(0xffffffffu, (v >> b) & 1u)) r |= (1u << b);
+  return r;
+}
 // 32 lanes x 16 consecutive fp32 columns of TMEM (the warp's own lane quarter)
 WETTS_DEVICE void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
@@ -127,6 +140,18 @@ WETTS_DEVICE void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// same load without the wait: issue several, then tmem_ld_wait() once
+WETTS_DEVICE void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+WETTS_DEVICE void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // warp-collective (call from one full warp)
 WETTS_DEVICE void tmem_alloc(uint32_t slot_smem_addr, uint32_t cols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem_addr), "r"(cols)
