@@ -311,6 +311,45 @@ __global__ void __launch_bounds__(kThreads) conv_post_kernel(const float* __rest
   }
 }
 
+// Same op for K = 7, T % 4 == 0: every thread produces 4 consecutive samples from three 16 B loads per
+// channel (its own quad plus the two neighbouring quads, which its neighbour threads also load: L1 hits), so
+// the kernel is a pure streaming read of the activation (HBM-bound) instead of one shared-memory load per FMA.
+__global__ void __launch_bounds__(kThreads) conv_post7_vec_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                                 float* __restrict__ out, int C, int T, float slope) {
+  extern __shared__ __align__(16) float wsm[];   // [C][8] (tap 7 = 0)
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < C * 8; i += kThreads) wsm[i] = ((i & 7) < 7) ? w[(i >> 3) * 7 + (i & 7)] : 0.f;
+  __syncthreads();
+  const int q = blockIdx.x * kThreads + tid;   // quad index
+  const int t4 = 4 * q;
+  if (t4 >= T) return;
+  const float* xb = in + (long long)b * C * T + t4;
+  const bool has_l = t4 >= 4, has_r = t4 + 8 <= T;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    const float* xc = xb + (long long)c * T;
+    const float4 l = has_l ? __ldg(reinterpret_cast<const float4*>(xc - 4)) : z4;
+    const float4 m = __ldg(reinterpret_cast<const float4*>(xc));
+    const float4 r = has_r ? __ldg(reinterpret_cast<const float4*>(xc + 4)) : z4;
+    float x[10] = {l.y, l.z, l.w, m.x, m.y, m.z, m.w, r.x, r.y, r.z};   // samples t4-3 .. t4+6
+#pragma unroll
+    for (int i = 0; i < 10; ++i) x[i] = x[i] > 0.f ? x[i] : x[i] * slope;
+    const float4 w0 = *reinterpret_cast<const float4*>(wsm + 8 * c);
+    const float4 w1 = *reinterpret_cast<const float4*>(wsm + 8 * c + 4);
+    const float wk[7] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z};
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      acc0 = fmaf(wk[k], x[k + 0], acc0);
+      acc1 = fmaf(wk[k], x[k + 1], acc1);
+      acc2 = fmaf(wk[k], x[k + 2], acc2);
+      acc3 = fmaf(wk[k], x[k + 3], acc3);
+    }
+  }
+  *reinterpret_cast<float4*>(out + (long long)b * T + t4) = make_float4(tanhf(acc0), tanhf(acc1), tanhf(acc2), tanhf(acc3));
+}
+
 }  // namespace
 
 void launch_conv1d(const ConvArgs& a, cudaStream_t s) {
@@ -348,6 +387,12 @@ void launch_conv_transpose1d(const ConvTArgs& a, cudaStream_t s) {
 
 void launch_conv_post_tanh(const float* in, const float* w, float* out, int B, int C, int T, int K, float slope,
                            cudaStream_t s) {
+  if (K == 7 && (T & 3) == 0 && C <= 512 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+    dim3 grid((T / 4 + kThreads - 1) / kThreads, B);
+    conv_post7_vec_kernel<<<grid, kThreads, (size_t)C * 8 * sizeof(float), s>>>(in, w, out, C, T, slope);
+    count_launch();
+    return;
+  }
   const size_t smem = sizeof(float) * ((size_t)kPostCi * (kPostTile + K - 1) + (size_t)C * K);
   static size_t configured = 0;
   if (smem > configured) {

@@ -29,7 +29,7 @@ __global__ void probe_dyn_smem_kernel(uint32_t* out) {
 
 }  // namespace
 
-static int dyn_smem_offset(uint32_t* off, cudaStream_t s) {
+int dyn_smem_offset(uint32_t* off, cudaStream_t s) {
   static int cached = -1;
   if (cached < 0) {
     uint32_t* d = nullptr;

@@ -55,6 +55,11 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(cons
   constexpr uint32_t TMEM_COLS = (6 * N <= 256) ? 256u : 512u;   // 3 accumulator blocks x [hi*hi | small terms]
   constexpr int CG = C / 4;
   constexpr int LOG_CG = (CG == 8) ? 3 : 4;
+  // With 16 warps the issuer (warp 0) and the weight producer (warp 1) do not stage activations: their global
+  // loads would sit between them and the tensor pipe.  The other 14 warps cover the tile exactly (448 x 2 units).
+  constexpr int SW0 = (C == 64) ? 2 : 0;                 // first staging warp
+  constexpr int STHREADS = THREADS - 32 * SW0;
+  static_assert(NU * STHREADS >= CG * (kFusedRbPitch / 4), "staging units do not cover the activation tile");
 
   WETTS_SMEM_DECL(smem);
   const int tid = WETTS_TID, lane = tid & 31;
@@ -111,9 +116,10 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(cons
     const int Hp = (H + 3) & ~3;
     const int Q = (128 + 2 * Hp) >> 2;
     const float* in_b = p.in + (long long)b * bs;
+    if (SW0 > 0 && warp < SW0) return;
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
-      const int u = tid + i * THREADS;
+      const int u = (tid - 32 * SW0) + i * STHREADS;
       const int cg = u & (CG - 1), q = u >> LOG_CG;
       const int t = t0 - Hp + 4 * q;
       const bool ok = (q < Q) && (t >= 0) && (t < T);     // T % 4 == 0 (checked on the host): a quad is all in or all out
@@ -138,9 +144,10 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(cons
     const int H = (p.d1[j] + p.d2[j]) * (p.k[j] - 1) / 2;
     const int Hp = (H + 3) & ~3;
     const int Q = (128 + 2 * Hp) >> 2;
+    if (SW0 > 0 && warp < SW0) return;
 #pragma unroll
     for (int i = 0; i < NU; ++i) {
-      const int u = tid + i * THREADS;
+      const int u = (tid - 32 * SW0) + i * STHREADS;
       const int cg = u & (CG - 1), q = u >> LOG_CG;
       if (q < Q) {
         split_store(cg, 4 * q + 0, lrelu(pf[i][0].x), lrelu(pf[i][1].x), lrelu(pf[i][2].x), lrelu(pf[i][3].x));

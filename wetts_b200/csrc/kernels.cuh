@@ -72,6 +72,9 @@ struct TcConvArgs {
   const float* wtc;
   int N, n_tiles, KC, n_chunks, MB, G, n_abuf, n_bbuf, R_pad, tmem_cols;
 };
+// Probes (once) the shared-window offset at which dynamic shared memory starts for kernels without static
+// shared memory.  tcgen05 descriptors built from this kernel parameter are uniform by construction.
+int dyn_smem_offset(uint32_t* off, cudaStream_t s);
 bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan);
 size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_abuf, int n_bbuf);
 void launch_pack_conv_tc(const float* src, float* dst, const int* co_map, const int* ci_map, int Cout, int Cin, int K,

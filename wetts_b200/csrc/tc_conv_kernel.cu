@@ -217,16 +217,35 @@ __device__ __forceinline__ void tc_epilogue_slice(const ConvArgs& a, int b, int 
     }
     case EPI_CONVT: {
       // polyphase ConvTranspose1d: packed channel = co*u + r, row t = input frame q; output sample
-      // n = q*u + r - pad of channel co (consecutive r are consecutive samples: coalesced)
+      // n = q*u + r - pad of channel co.  The u phases of one (q, co) are u consecutive samples, so a slice of
+      // 16 packed channels is 16/u runs of u contiguous floats: written with 8 / 16 B stores when the run is
+      // inside the signal and suitably aligned (u = 4: pad 2 -> 8 B; u = 8: pad 4 -> 16 B), else sample by sample.
       const int u = e.up_u;
       const long long n0 = (long long)t * u - e.up_pad;
       float* ob = e.out + (size_t)b * (size_t)e.out_bs;
+      const bool whole = (nval == 16) && (n0 >= 0) && (n0 + u <= e.out_T) && ((e.out_T & 3) == 0);
+      if (u == 8 && whole && (co0 & 7) == 0 && (n0 & 3) == 0) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int cp = co0 + i;
-        const int co = cp / u, r = cp - co * u;
-        const long long n = n0 + r;
-        if (i < nval && n >= 0 && n < e.out_T) ob[(size_t)co * (size_t)e.out_T + (size_t)n] = v[i];
+        for (int i = 0; i < 16; i += 8) {
+          float4* dst = reinterpret_cast<float4*>(ob + (size_t)((co0 + i) >> 3) * (size_t)e.out_T + (size_t)n0);
+          dst[0] = make_float4(v[i + 0], v[i + 1], v[i + 2], v[i + 3]);
+          dst[1] = make_float4(v[i + 4], v[i + 5], v[i + 6], v[i + 7]);
+        }
+      } else if (u == 4 && whole && (co0 & 3) == 0 && (n0 & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float2* dst = reinterpret_cast<float2*>(ob + (size_t)((co0 + i) >> 2) * (size_t)e.out_T + (size_t)n0);
+          dst[0] = make_float2(v[i + 0], v[i + 1]);
+          dst[1] = make_float2(v[i + 2], v[i + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int cp = co0 + i;
+          const int co = cp / u, r = cp - co * u;
+          const long long n = n0 + r;
+          if (i < nval && n >= 0 && n < e.out_T) ob[(size_t)co * (size_t)e.out_T + (size_t)n] = v[i];
+        }
       }
       break;
     }
