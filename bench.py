@@ -108,6 +108,18 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(workload):
+    """DRAM bytes per generator call from the committed ncu capture (profiles/generator_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "generator_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d.get("workload") == workload:
+            return float(d["generator_dram_bytes_per_step"]), d.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
 def pick_cpu_threads(workload):
     """oneDNN convs on tiny channel counts degrade when oversubscribed: try a few thread counts on one
     utterance and keep the fastest (reported as `cores`)."""
@@ -299,6 +311,7 @@ def run_ours(args):
         all_frames = B * Ty                                    # the generator runs the padded tail too (finding 9)
         gen_bytes = GEN_LAYER_BYTES_PER_FRAME[cfg_name] * all_frames
         gen_flop = GEN_FLOP_PER_FRAME[cfg_name] * all_frames
+        traffic, traffic_src = measured_traffic(args.workload) if (B, args.fused_resblock, args.tensor_cores) == (WORKLOADS[args.workload][3], 1, 1) else (None, None)
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12        # TFLOP/s at the clock seen under load
         line = {
@@ -318,7 +331,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "HiFi-GAN generator conv stack (wetts_generator_forward)",
                          "achieved": gen_bytes / (gen_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": gen_bytes / (gen_ms / 1e3) / 1e9 / hbm_peak, "traffic": None,
+                         "frac": gen_bytes / (gen_ms / 1e3) / 1e9 / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "algorithmic_bytes": gen_bytes,
                          "bytes": "layer-boundary algorithmic bytes (BASELINE.md §4)", "peak_source": which,
                          "ms": gen_ms,
                          "fp32_fma": {"achieved": gen_flop / (gen_ms / 1e3) / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",

@@ -1,13 +1,14 @@
 #!/bin/bash
-# ncu --set full capture of selected tcgen05 conv launches inside the timed step: pairs of (skip, name)
+# Profiling visit: (a) DRAM bytes + duration of every launch of one timed step (full batch), (b) ncu --set full
+# capture of the two fused MRF stage kernels (batch 64 to keep the replay short).
 set -x
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-while [ $# -ge 2 ]; do
-  SKIP=$1; NAME=$2; shift 2
-  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-     -k regex:conv1d_tc_kernel -s $SKIP -c 1 -o gpurun_out/$NAME -f \
-     python bench.py --steps 1 --warmup 3 --no-cpu --profile-range --batch 64 > gpurun_out/ncu_full_$NAME.log 2>&1
-  tail -n 2 gpurun_out/ncu_full_$NAME.log
-done
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    --profile-from-start off --csv --log-file gpurun_out/dram.csv \
+    python bench.py --steps 1 --warmup 3 --no-cpu --profile-range > gpurun_out/ncu_dram.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:fused_resblock2 -c 2 -o gpurun_out/fused_rb -f \
+    python bench.py --steps 1 --warmup 3 --no-cpu --profile-range --batch 64 > gpurun_out/ncu_full.log 2>&1
+tail -n 2 gpurun_out/ncu_full.log
 ls -la gpurun_out/*.ncu-rep
