@@ -350,7 +350,45 @@ __global__ void __launch_bounds__(kThreads) conv_post7_vec_kernel(const float* _
   *reinterpret_cast<float4*>(out + (long long)b * T + t4) = make_float4(tanhf(acc0), tanhf(acc1), tanhf(acc2), tanhf(acc3));
 }
 
+// Per-utterance conditioning vectors out[b][co] = bias[co] + sum_ci W[co][ci] g[b][ci] (a 1x1 conv over T = 1,
+// i.e. a small GEMM over the batch).  Block = 64 output channels x 16 utterances; w is the SIMT layout
+// [Cin][1][CoutPad] (output channel contiguous: coalesced), g is staged in shared memory.
+constexpr int kCondB = 16;
+__global__ void __launch_bounds__(256) cond_vec_kernel(const float* __restrict__ g, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ out, int B,
+                                                       int Cin, int Cout, int CoutPad) {
+  extern __shared__ float gs[];   // [kCondB][Cin]
+  const int co = blockIdx.x * 64 + (threadIdx.x & 63), bq = threadIdx.x >> 6, b0 = blockIdx.y * kCondB;
+  for (int i = threadIdx.x; i < kCondB * Cin; i += 256) {
+    const int b = b0 + i / Cin;
+    gs[i] = b < B ? g[(long long)b * Cin + (i % Cin)] : 0.f;
+  }
+  __syncthreads();
+  if (co >= Cout) return;
+  float acc[4];
+  const float bv = bias ? bias[co] : 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = bv;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float wv = __ldg(w + (long long)ci * CoutPad + co);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = fmaf(wv, gs[(bq * 4 + j) * Cin + ci], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int b = b0 + bq * 4 + j;
+    if (b < B) out[(long long)b * Cout + co] = acc[j];
+  }
+}
+
 }  // namespace
+
+void launch_cond_vector(const float* g, const float* w, const float* bias, float* out, int B, int Cin, int Cout,
+                        int CoutPad, cudaStream_t s) {
+  dim3 grid((Cout + 63) / 64, (B + kCondB - 1) / kCondB);
+  cond_vec_kernel<<<grid, 256, (size_t)kCondB * Cin * sizeof(float), s>>>(g, w, bias, out, B, Cin, Cout, CoutPad);
+  count_launch();
+}
 
 void launch_conv1d(const ConvArgs& a, cudaStream_t s) {
   if (a.wtc && a.T >= 64 && a.dil == a.tc.dil && tensor_cores_enabled()) launch_conv1d_tc(a, s);

@@ -287,6 +287,10 @@ static ConvArgs conv_args(const Conv& c, const float* in, long long in_bs, int i
 
 // per-(b, co) vector from g: out[b][co] = W g[b] + bias   (a Conv1d over T == 1)
 static void cond_vector(const Conv& c, const float* g, int B, float* out, cudaStream_t s) {
+  if (c.K == 1 && c.Cin * 16 * sizeof(float) <= 48 * 1024) {
+    launch_cond_vector(g, c.w, c.b, out, B, c.Cin, c.Cout, c.CoutPad, s);
+    return;
+  }
   ConvArgs a = conv_args(c, g, c.Cin, 1, B, 1);
   a.ep.out = out;
   a.ep.out_bs = c.Cout;

@@ -65,6 +65,9 @@ struct ConvArgs {
   ConvEpilogue ep;
 };
 void launch_conv1d(const ConvArgs& a, cudaStream_t s);
+// out[b][co] = bias[co] + sum_ci w[ci][co] g[b][ci]   (w: SIMT layout of a 1x1 conv, [Cin][1][CoutPad])
+void launch_cond_vector(const float* g, const float* w, const float* bias, float* out, int B, int Cin, int Cout,
+                        int CoutPad, cudaStream_t s);
 void launch_conv1d_simt(const ConvArgs& a, cudaStream_t s);
 
 struct TcConvArgs {
