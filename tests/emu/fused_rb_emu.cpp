@@ -1,7 +1,7 @@
 // CPU check of fused_resblock2_kernel (wetts_b200/csrc/fused_rb_kernel.cuh) in the CTA emulator:
 // the kernel source is compiled for the host and compared with a direct fp64 evaluation of
 // ResBlock2 x nrb + MRF mean (decoders.py:205-214, :72-76).
-//   usage: fused_rb_emu C B T grid [nrb]
+//   usage: fused_rb_emu C B T grid [nrb] [ring slots: 4 | 6]
 #define WETTS_EMULATE 1
 #include <math.h>
 
@@ -28,7 +28,7 @@ static void conv_ref(const std::vector<double>& x, std::vector<double>& y, const
     }
 }
 
-template <int C, int THREADS>
+template <int C, int THREADS, int NB>
 static int run(int B, int T, int grid, int nrb) {
   const int ks[3] = {3, 5, 7}, d1s[3] = {1, 2, 3}, d2s[3] = {2, 6, 12};
   std::mt19937 rng(1234 + C + T);
@@ -57,7 +57,8 @@ static int run(int B, int T, int grid, int nrb) {
   fused_rb_finalize_args(a, C);
   if (a.Rp < 128 + 2 * ((Hmax + 3) & ~3) || (a.Rp & 1) == 0) { printf("Rp mismatch\n"); return 1; }
   if ((size_t)a.nq * fused_rb_chunk_floats(C) != packed_floats) { printf("chunk accounting mismatch\n"); return 1; }
-  if (fused_rb_smem_bytes(C, a.Rp) > emu::kSmemBytes) { printf("smem over budget\n"); return 1; }
+  if (NB == 6 && a.nq % 6 != 0) { printf("6-slot ring needs nq %% 6 == 0 (nq = %d)\n", a.nq); return 64; }
+  if (fused_rb_smem_bytes(C, NB) > emu::kSmemBytes) { printf("smem over budget\n"); return 1; }
   // pack: conv order j0.c1, j0.c2, j1.c1, ... exactly as the engine does
   float* packed = (float*)aligned_alloc(128, packed_floats * 4);
   {
@@ -78,7 +79,7 @@ static int run(int B, int T, int grid, int nrb) {
   a.in = x.data(); a.out = out.data(); a.w = packed;
   a.smem_off = emu::kSmemBase;
   unsigned long long n_mma = 0;
-  emu::launch(fused_resblock2_kernel<C, THREADS, 1>, a, grid, THREADS, &n_mma);
+  emu::launch(fused_resblock2_kernel<C, THREADS, 1, NB>, a, grid, THREADS, &n_mma);
 
   // reference
   double max_err = 0, sq = 0;
@@ -99,17 +100,20 @@ static int run(int B, int T, int grid, int nrb) {
     }
   }
   const double rms = sqrt(sq / ((double)B * C * T));
-  printf("C=%d B=%d T=%d grid=%d nrb=%d: mma=%llu max_err=%.3e rms=%.3e rel=%.3e\n", C, B, T, grid, nrb, n_mma, max_err, rms,
+  printf("C=%d ring=%d B=%d T=%d grid=%d nrb=%d: mma=%llu max_err=%.3e rms=%.3e rel=%.3e\n", C, NB, B, T, grid, nrb, n_mma, max_err, rms,
          max_err / rms);
   free(packed);
   return (max_err / rms < 2e-5) ? 0 : 2;
 }
 
 int main(int argc, char** argv) {
-  if (argc < 5) { printf("usage: %s C B T grid [nrb]\n", argv[0]); return 64; }
+  if (argc < 5) { printf("usage: %s C B T grid [nrb] [ring]\n", argv[0]); return 64; }
   const int C = atoi(argv[1]), B = atoi(argv[2]), T = atoi(argv[3]), grid = atoi(argv[4]);
   const int nrb = argc > 5 ? atoi(argv[5]) : 3;
-  if (C == 32) return run<32, 256>(B, T, grid, nrb);
-  if (C == 64) return run<64, 512>(B, T, grid, nrb);
+  const int ring = argc > 6 ? atoi(argv[6]) : 4;
+  if (C == 32 && ring == 4) return run<32, 256, 4>(B, T, grid, nrb);
+  if (C == 32 && ring == 6) return run<32, 256, 6>(B, T, grid, nrb);
+  if (C == 64 && ring == 4) return run<64, 512, 4>(B, T, grid, nrb);
+  if (C == 64 && ring == 6) return run<64, 512, 6>(B, T, grid, nrb);
   return 64;
 }

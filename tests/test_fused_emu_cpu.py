@@ -28,9 +28,10 @@ def emu_binary(tmp_path_factory):
     return out
 
 
-# (C, B, T, grid, nrb): ragged last tile, single short tile, more CTAs than items, 1-3 resblocks, both widths
-CASES = [(32, 2, 300, 2, 3), (32, 1, 76, 1, 3), (32, 2, 256, 5, 1), (32, 2, 520, 3, 2),
-         (64, 2, 300, 2, 3), (64, 1, 640, 2, 3), (64, 3, 320, 4, 2)]
+# (C, B, T, grid, nrb, ring slots): ragged last tile, single short tile, more CTAs than items, 1-3 resblocks,
+# both widths, both ring sizes (6 slots need a chunk count per item that is a multiple of 6: nrb = 3 or 1 here)
+CASES = [(32, 2, 300, 2, 3, 4), (32, 1, 76, 1, 3, 6), (32, 2, 256, 5, 1, 6), (32, 2, 520, 3, 2, 4),
+         (64, 2, 300, 2, 3, 6), (64, 1, 640, 2, 3, 4), (64, 3, 320, 4, 2, 4), (32, 2, 1000, 3, 3, 6)]
 
 
 @pytest.mark.parametrize("case", CASES)

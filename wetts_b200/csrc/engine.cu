@@ -1002,7 +1002,7 @@ int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_len
     const int ch = up.Cout;
     const long long bs = (long long)ch * len;
     float* acc = w.x[cur ^ 1];
-    if (h->fused_rb_w[i] && tensor_cores_enabled() && fused_resblock_enabled()) {
+    if (h->fused_rb_w[i] && tensor_cores_enabled() && fused_resblock_enabled() && (len & 3) == 0) {   // 16 B row loads
       FusedRbArgs fa;
       fa.in = w.xu; fa.out = acc; fa.w = h->fused_rb_w[i];
       fa.B = B; fa.T = len; fa.nrb = nk; fa.slope = 0.1f; fa.div = (float)nk;

@@ -70,34 +70,45 @@ void launch_fused_rb_pack(const float* w_folded, float* dst, int C, int K, cudaS
   count_launch();
 }
 
+template <int C, int THREADS, int MINB, int NB, bool PROFILE>
+static int launch_variant(const FusedRbArgs& a, int grid, size_t smem, cudaStream_t s) {
+  static size_t configured = 0;
+  auto kern = fused_resblock2_kernel<C, THREADS, MINB, NB, PROFILE>;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    configured = smem;
+  }
+  kern<<<grid, THREADS, smem, s>>>(a);
+  count_launch();
+  return 0;
+}
+template <bool PROFILE>
+static int launch_any(int C, int ring, const FusedRbArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (C == 32) return ring == 6 ? launch_variant<32, 256, 2, 6, PROFILE>(a, grid, smem, s) : launch_variant<32, 256, 2, 4, PROFILE>(a, grid, smem, s);
+  if (C == 64) return ring == 6 ? launch_variant<64, 512, 1, 6, PROFILE>(a, grid, smem, s) : launch_variant<64, 512, 1, 4, PROFILE>(a, grid, smem, s);
+  return 1;
+}
+
 // Debug path (WETTS_FUSED_RB_PROFILE=1): the clock64-instrumented instantiation, phase table to stderr.
-static int launch_fused_rb_profiled(int C, FusedRbArgs a, size_t smem, int n_sm, long long items, cudaStream_t s) {
+static int launch_fused_rb_profiled(int C, int ring, FusedRbArgs a, int grid, size_t smem, long long items, cudaStream_t s) {
   static const char* names[kFusedRbProfPhases] = {"stage", "sync+prefetch", "conv1 issue", "conv1 wait", "epi1", "sync",
                                                   "conv2 issue", "conv2 wait", "epi2", "end sync", "loop", "[conv1 rb0", "conv1 rb1", "conv1 rb2", "full-wait]"};
-  const int grid = (int)(C == 32 ? (items < 2 * n_sm ? items : 2 * n_sm) : (items < n_sm ? items : n_sm));
   const size_t n = (size_t)grid * 2 * kFusedRbProfPhases;
   long long* d = nullptr;
   if (cudaMalloc(&d, n * sizeof(long long)) != cudaSuccess) return 1;
   cudaMemsetAsync(d, 0, n * sizeof(long long), s);
   a.prof = d;
-  if (C == 32) {
-    cudaFuncSetAttribute(fused_resblock2_kernel<32, 256, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    fused_resblock2_kernel<32, 256, 2, true><<<grid, 256, smem, s>>>(a);
-  } else {
-    cudaFuncSetAttribute(fused_resblock2_kernel<64, 512, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    fused_resblock2_kernel<64, 512, 1, true><<<grid, 512, smem, s>>>(a);
-  }
-  count_launch();
+  if (launch_any<true>(C, ring, a, grid, smem, s)) return 1;
   if (cudaStreamSynchronize(s) != cudaSuccess) return 1;
   std::vector<long long> h(n);
   cudaMemcpy(h.data(), d, n * sizeof(long long), cudaMemcpyDeviceToHost);
   cudaFree(d);
   const double per_cta_items = (double)items / grid;
-  fprintf(stderr, "[fused_rb profile] C=%d B=%d T=%d grid=%d items/CTA=%.1f  (cycles per item, mean over CTAs)\n", C, a.B, a.T, grid,
-          per_cta_items);
+  fprintf(stderr, "[fused_rb profile] C=%d ring=%d B=%d T=%d grid=%d items/CTA=%.1f  (cycles per item, mean over CTAs)\n", C, ring,
+          a.B, a.T, grid, per_cta_items);
   for (int who = 0; who < 2; ++who) {
     double tot = 0;
-    fprintf(stderr, "  %s:", who ? "thread 32 (epilogue warp)" : "thread 0 (MMA issuer)   ");
+    fprintf(stderr, "  %s:", who ? "thread 32 (producer warp)" : "thread 0 (MMA issuer)   ");
     for (int i = 0; i < kFusedRbProfPhases; ++i) {
       double sum = 0;
       for (int b = 0; b < grid; ++b) sum += (double)h[((size_t)b * 2 + who) * kFusedRbProfPhases + i];
@@ -111,37 +122,24 @@ static int launch_fused_rb_profiled(int C, FusedRbArgs a, size_t smem, int n_sm,
 }
 
 int launch_fused_rb(int C, FusedRbArgs a, cudaStream_t s) {
+  if ((a.T & 3) != 0 || (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.w) & 15) != 0) return 1;   // 16 B loads / bulk copies
   fused_rb_finalize_args(a, C);
   if (dyn_smem_offset(&a.smem_off, s)) return 1;
-  const size_t smem = fused_rb_smem_bytes(C, a.Rp);
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   }
+  const char* force = getenv("WETTS_FUSED_RB_RING");
+  const int ring = force ? atoi(force) : fused_rb_ring_slots(a.nq);
+  if (ring != 4 && !(ring == 6 && a.nq % 6 == 0)) return 1;
+  const size_t smem = fused_rb_smem_bytes(C, ring);
   const long long items = (long long)a.B * ((a.T + 127) / 128);
-  if (getenv("WETTS_FUSED_RB_PROFILE")) return launch_fused_rb_profiled(C, a, smem, n_sm, items, s);
-  static size_t configured[2] = {0, 0};
-  if (C == 32) {
-    if (smem > configured[0]) {
-      if (cudaFuncSetAttribute(fused_resblock2_kernel<32, 256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-      configured[0] = smem;
-    }
-    const int grid = (int)(items < 2 * n_sm ? items : 2 * n_sm);
-    fused_resblock2_kernel<32, 256, 2><<<grid, 256, smem, s>>>(a);
-  } else if (C == 64) {
-    if (smem > configured[1]) {
-      if (cudaFuncSetAttribute(fused_resblock2_kernel<64, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-      configured[1] = smem;
-    }
-    const int grid = (int)(items < n_sm ? items : n_sm);
-    fused_resblock2_kernel<64, 512, 1><<<grid, 512, smem, s>>>(a);
-  } else {
-    return 1;
-  }
-  count_launch();
-  return 0;
+  const int per_sm = (C == 32) ? 2 : 1;
+  const int grid = (int)(items < (long long)per_sm * n_sm ? items : (long long)per_sm * n_sm);
+  if (getenv("WETTS_FUSED_RB_PROFILE")) return launch_fused_rb_profiled(C, ring, a, grid, smem, items, s);
+  return launch_any<false>(C, ring, a, grid, smem, s);
 }
 
 }  // namespace wetts

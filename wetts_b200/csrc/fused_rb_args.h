@@ -22,6 +22,7 @@ struct FusedRbArgs {
   int k[3] = {0, 0, 0}, d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};
   int Rp = 0;                  // row pitch of a channel group in the activation buffer: >= 128 + 2*max_j Hp_j, odd
   int nq = 0;                  // weight chunks per item = sum_j 2*k_j*(C/32)
+  int nq_ring = 0;             // nq / ring slots when the ring size divides nq (6-slot ring), else 0
   int qoff[6] = {0, 0, 0, 0, 0, 0};  // first chunk (within the item) of conv 2*j + {0: conv1, 1: conv2}
   uint32_t smem_off = 0;       // CTA-local shared-window offset of the dynamic shared memory base (see the kernel)
   float slope = 0.1f;
@@ -30,15 +31,16 @@ struct FusedRbArgs {
 };
 constexpr int kFusedRbProfPhases = 15;
 
-constexpr int kFusedRbRing = 4;      // weight ring slots (power of two: slot and phase are bit fields of the chunk number)
-constexpr int kFusedRbAhead = 4;     // chunks requested ahead of the MMAs (= ring: a slot is refilled the moment its chunk completes)
 constexpr int kFusedRbPitch = 225;   // rows per 4-channel group of the activation tile (odd; >= 128 + 2*48 halo rows)
 constexpr int kFusedRbUnits = 2;     // (4 rows x 4 channels) staging units per thread  ->  R <= 256 rows
 
 // floats of one weight chunk: [8 k-groups][hi|lo][N][4]  (hi and lo rows adjacent: one 2N-row operand)
 constexpr int fused_rb_chunk_floats(int C) { return 2 * 8 * C * 4; }
-inline size_t fused_rb_smem_bytes(int C, int Rp = kFusedRbPitch) {
-  return 128 + (size_t)kFusedRbRing * fused_rb_chunk_floats(C) * 4 + 6 * (size_t)C * 4 + 2 * (size_t)C * Rp * 4;
+// weight ring slots: 6 when the chunk count per item is a multiple of 6 (slot index then depends on the chunk's
+// position in the item only), else 4 (slot and phase are bit fields of the global chunk number)
+inline int fused_rb_ring_slots(int nq) { return (nq % 6 == 0) ? 6 : 4; }
+inline size_t fused_rb_smem_bytes(int C, int ring, int Rp = kFusedRbPitch) {
+  return 128 + (size_t)ring * fused_rb_chunk_floats(C) * 4 + 6 * (size_t)C * 4 + 2 * (size_t)C * Rp * 4;
 }
 // Derived launch fields (Rp, nq, qoff) from (nrb, k, d1, d2).
 inline void fused_rb_finalize_args(FusedRbArgs& a, int C) {
@@ -53,6 +55,7 @@ inline void fused_rb_finalize_args(FusedRbArgs& a, int C) {
     a.qoff[2 * j + 1] = a.nq;
     a.nq += a.k[j] * (C / 32);
   }
+  a.nq_ring = (a.nq % 6 == 0) ? a.nq / 6 : 0;
   a.Rp = kFusedRbPitch;   // compile-time pitch; fused_rb_supported() guarantees 128 + 2*Hmax <= pitch
   (void)Hmax;
 }

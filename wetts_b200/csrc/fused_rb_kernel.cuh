@@ -43,13 +43,15 @@ namespace wetts {
 
 // PROFILE = true adds clock64 phase timers (thread 0 = the MMA issuer, thread 32 = the producer warp),
 // summed per CTA into p.prof[cta][2][kFusedRbProfPhases]; used by tools/, never by the product path.
-template <int C, int THREADS, int MINB, bool PROFILE = false>
+// NB = weight ring slots: 4 (any chunk count) or 6 (needs nq % 6 == 0; 50 % more look-ahead).
+template <int C, int THREADS, int MINB, int NB = 4, bool PROFILE = false>
 WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(const FusedRbArgs p) {
   using namespace tc;
   static_assert(C == 32 || C == 64, "channel count");
   static_assert(THREADS == 8 * C, "8 warps for C = 32, 16 warps for C = 64");
   constexpr int N = C;
-  constexpr int NB = kFusedRbRing, PD = kFusedRbAhead, NU = kFusedRbUnits;
+  static_assert(NB == 4 || NB == 6, "ring size");
+  constexpr int PD = NB, NU = kFusedRbUnits;   // a slot is refilled the moment its chunk completes
   constexpr int KH = C / 32;
   constexpr uint32_t CHUNK_BYTES = 8u * 2u * N * 16u;     // [8 k-groups][hi|lo][N][4 floats]
   constexpr uint32_t TMEM_COLS = (6 * N <= 256) ? 256u : 512u;   // 3 accumulator blocks x [hi*hi | small terms]
@@ -178,16 +180,28 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(cons
   // Chunk number g = it*nq + q (q = index within the item) is pure arithmetic on loop counters and kernel
   // parameters, so slot = g % NB, phase = g / NB and every descriptor derived from them stay in uniform
   // registers: the tcgen05.mma operands need no R2UR (the issue loop is otherwise ~90 cycles per MMA).
-  static_assert((NB & (NB - 1)) == 0, "ring size must be a power of two");
-  constexpr uint32_t LOG_NB = (NB == 2) ? 1u : (NB == 4) ? 2u : 3u;
   const uint32_t nq = (uint32_t)p.nq;
+  // (slot, number of earlier uses of the slot) of chunk q of this CTA's it-th item.  NB = 4: bit fields of
+  // the chunk number.  NB = 6: nq is a multiple of 6 (host-checked), so the slot depends on q only;
+  // q / 6 = (q * 171) >> 10 holds for q < 500.
+  auto ring_pos = [&](uint32_t it_, uint32_t q_, uint32_t& slot, uint32_t& use) {
+    if (NB == 4) {
+      const uint32_t g = it_ * nq + q_;
+      slot = g & 3u;
+      use = g >> 2;
+    } else {
+      const uint32_t qd = (q_ * 171u) >> 10;
+      slot = q_ - 6u * qd;
+      use = it_ * (uint32_t)p.nq_ring + qd;
+    }
+  };
   // producer (warp 1, warp-uniform): request chunk q_p of this CTA's it_p-th item into slot g % NB once the
   // MMAs that read the slot's previous occupant (chunk g - NB) have completed
   auto produce = [&](uint32_t it_p, uint32_t q_p) {
     if (q_p >= nq) { q_p -= nq; it_p += 1; }
     if (it_p >= (uint32_t)my_items) return;
-    const uint32_t g = it_p * nq + q_p;
-    const uint32_t slot = g & (uint32_t)(NB - 1), use = g >> LOG_NB;
+    uint32_t slot, use;
+    ring_pos(it_p, q_p, slot, use);
     if (use > 0) mbar_wait(bar_empty + 8 * slot, (use - 1) & 1);
     // no lane may still be inside the parity wait when the slot is handed back to the MMA warp: the barrier
     // could then complete a second phase and the late lane would wait for a parity that never returns
@@ -227,8 +241,9 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(cons
     for (int tap = 0; tap < k; ++tap) {
       for (int kh = 0; kh < KH; ++kh) {
         const uint32_t q = qbase + (uint32_t)(tap * KH + kh);
-        const uint32_t g = it * nq + q;
-        const uint32_t slot = g & (uint32_t)(NB - 1), par = (g >> LOG_NB) & 1u;
+        uint32_t slot, use;
+        ring_pos(it, q, slot, use);
+        const uint32_t par = use & 1u;
         long long tw = 0;
         if (PROFILE) tw = clock_now();
         mbar_wait(bar_full + 8 * slot, par);
