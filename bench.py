@@ -28,9 +28,9 @@ sys.path.insert(0, ROOT)
 # workload -> (config, n_vocab, n_speakers, batch per GPU, phonemes, length_scale, cpu sample utterances)
 WORKLOADS = {
     # BASELINE.json configs[2]: the configuration the metric is quoted on (batch 256 x 128 phonemes, full infer)
-    "multilingual_v3_b256x128": ("multilingual_v3", 256, 2, 256, 128, 2.8, 8),
+    "multilingual_v3_b256x128": ("multilingual_v3", 256, 2, 256, 128, 2.8, 48),
     # BASELINE.json configs[1]-like full path on the heavy HiFi-GAN V1 generator
-    "baker_v1_b64x128": ("baker_v1", 256, 1, 64, 128, 3.4, 2),
+    "baker_v1_b64x128": ("baker_v1", 256, 1, 64, 128, 3.4, 4),
     # small smoke-sized workload
     "multilingual_v3_b8x32": ("multilingual_v3", 256, 2, 8, 32, 2.8, 8),
 }

@@ -247,6 +247,11 @@ WETTS_DEVICE void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32
   std::lock_guard<std::mutex> g(emu::cta()->m);
   emu::cta()->copies.push_back({dst, bytes, bar, src});
 }
+WETTS_DEVICE uint64_t l2_policy_evict_last() { return 0; }
+WETTS_DEVICE void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t) {
+  bulk_g2s(dst, src, bytes, bar);
+}
+WETTS_DEVICE void st_streaming(float* p, float v) { *p = v; }
 WETTS_DEVICE void fence_async_smem() {}
 WETTS_DEVICE void tc_fence_before() {}
 WETTS_DEVICE void tc_fence_after() {}

@@ -181,6 +181,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(cons
   // parameters, so slot = g % NB, phase = g / NB and every descriptor derived from them stay in uniform
   // registers: the tcgen05.mma operands need no R2UR (the issue loop is otherwise ~90 cycles per MMA).
   const uint32_t nq = (uint32_t)p.nq;
+  const uint64_t w_policy = l2_policy_evict_last();   // weights stay L2-resident under the activation stream
   // (slot, number of earlier uses of the slot) of chunk q of this CTA's it-th item.  NB = 4: bit fields of
   // the chunk number.  NB = 6: nq is a multiple of 6 (host-checked), so the slot depends on q only;
   // q / 6 = (q * 171) >> 10 holds for q < 500.
@@ -208,8 +209,8 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(cons
     warp_sync();
     if (elect_one()) {
       mbar_expect_tx(bar_full + 8 * slot, CHUNK_BYTES);
-      bulk_g2s(ring_addr + slot * CHUNK_BYTES, reinterpret_cast<const uint8_t*>(p.w) + (size_t)q_p * CHUNK_BYTES,
-               CHUNK_BYTES, bar_full + 8 * slot);
+      bulk_g2s_hint(ring_addr + slot * CHUNK_BYTES, reinterpret_cast<const uint8_t*>(p.w) + (size_t)q_p * CHUNK_BYTES,
+                    CHUNK_BYTES, bar_full + 8 * slot, w_policy);
     }
     warp_sync();
   };
@@ -399,7 +400,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_resblock2_kernel(cons
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float sum = (v[i] + vs[i]) + racc[i];
-            op[(long long)i * T] = (nrb > 1) ? sum / p.div : sum;
+            st_streaming(op + (long long)i * T, (nrb > 1) ? sum / p.div : sum);
           }
         }
       }

@@ -67,6 +67,20 @@ WETTS_DEVICE void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// L2 cache policies: the weight stream is re-read by every CTA for every work item and must survive the
+// multi-GB activation stream that flows through the same L2 (evict_last); outputs are written once (stcs).
+WETTS_DEVICE uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+WETTS_DEVICE void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+WETTS_DEVICE void st_streaming(float* p, float v) { __stcs(p, v); }
 WETTS_DEVICE void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 WETTS_DEVICE void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 WETTS_DEVICE void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
