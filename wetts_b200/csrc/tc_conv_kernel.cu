@@ -23,118 +23,13 @@
 
 #include "epilogue.cuh"
 #include "kernels.cuh"
+#include "tc_prims.cuh"
 
 namespace wetts {
 namespace {
 
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-// Bounded spin: a pipeline bug must fail fast (trap + message) instead of hanging the GPU.
-__device__ __noinline__ void mbar_timeout(uint32_t bar, uint32_t parity) {
-  printf("wetts_b200: mbarrier wait timed out (smem 0x%x, parity %u, block %d, thread %d)\n", bar, parity,
-         (int)blockIdx.x, (int)threadIdx.x);
-  __trap();
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  uint32_t spins = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && ++spins > (1u << 24)) mbar_timeout(bar, parity);
-  } while (!done);
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// The three 3xTF32 MMAs of one (tap, k-step) issued by one elected lane WITHOUT a C++ branch: the
-// election and the predication live inside the asm block, so the surrounding loop is straight-line
-// warp-uniform code (no BSSY/BSYNC reconvergence, operands stay uniform).
-__device__ __forceinline__ void tc_mma_tf32_x3(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo,
-                                               uint32_t idesc, uint32_t accumulate_first) {
-  asm volatile(
-      "{\n\t.reg .pred pe, pa;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "setp.ne.b32 pa, %6, 0;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %2, %3, %5, pa;\n\t"    // lo * hi (small terms first)
-      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %4, %5, 1;\n\t"     // hi * lo
-      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %3, %5, 1;\n\t}"    // hi * hi
-      ::"r"(d_tmem), "l"(a_hi), "l"(a_lo), "l"(b_hi), "l"(b_lo), "r"(idesc), "r"(accumulate_first)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
-// shared-memory matrix descriptor: K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-
-// true in exactly one (converged) lane of the warp; keeps the surrounding control flow warp-uniform so
-// that descriptors and addresses stay in uniform registers (no per-MMA R2UR waterfall)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint64_t desc_with_lo(uint64_t base, uint32_t lo) {
-  return (base & 0xFFFFFFFF00000000ull) | (uint64_t)lo;
-}
+using namespace tc;   // PTX wrappers shared with the fused kernels (tc_prims.cuh)
 
 // Fused epilogue of one 16-channel slice of one output row, specialised per mode with the switch
 // hoisted out of the element loops: all global loads of the slice are issued before the first store.
@@ -283,7 +178,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
   constexpr int FIRST_MMA_WARP = THREADS / 32 - NI;
   extern __shared__ __align__(128) uint8_t smem[];
   const ConvArgs& a = p.c;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Issue-path hygiene (see DESIGN.md 4.1 "Issue path"; verified in SASS: UTCHMMA operands without R2UR):
+  //  * warp index and TMEM base are rebuilt from warp votes (provably uniform);
+  //  * mbarrier waits are single asm statements (tc_prims.cuh);
+  //  * the MMA warp and the staging warps keep SEPARATE pipeline counters (a_count / a_count_s): a variable
+  //    that is also updated inside the thread-dependent staging loops is "divergent" for the compiler, and
+  //    through it every descriptor of the MMA loop was (308 predicated R2UR before, 2 after).
+  const int tid = threadIdx.x, lane = tid & 31, warp = (int)uniform_bits((uint32_t)(tid >> 5), 0, 4);
   const int K = a.K, dil = a.dil, T = a.T;
   const int N = p.N, KC = p.KC, MB = p.MB, MT = 128 * p.MB;
   const int R = MT + (K - 1) * dil;
@@ -308,10 +209,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
   const uint32_t A_addr = smem_u32(A0), B_addr = smem_u32(B0);
 
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   }
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);   // a_free[2], b_full[2]
@@ -325,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_bits(*tmem_slot, 5, 9);
 
   const int G = p.G;
   const int group_rows = G * MT;
@@ -337,7 +235,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
   uint32_t a_fills0 = 0, a_fills1 = 0, b_loads0 = 0, b_loads1 = 0, b_count = 0;   // MMA lane
   int b_resident_nt = -1;
   uint32_t a_uses0 = 0, a_uses1 = 0;                                              // stagers
-  uint32_t a_count = 0, acc_count = 0, item_count = 0;
+  uint32_t a_count = 0, a_count_s = 0, acc_count = 0, item_count = 0;
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t a_lo_delta = a_half >> 4, b_lo_delta = b_half >> 4;
   const int nb16 = (KC + 15) / 16;
@@ -373,7 +271,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
 
     if (warp >= FIRST_MMA_WARP) {
       // ============ tensor-pipe warps: uniform control flow, one elected lane per warp issues ============
-      const int iw = warp - FIRST_MMA_WARP;
+      constexpr int iw = 0;   // NI == 1: the issuer index is a constant, not a function of the warp index
+      static_assert(NI == 1, "one issuing warp");
       {
         for (int c = 0; c < p.n_chunks; ++c) {
           int bb = 0;
@@ -467,7 +366,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
         const int c0 = c * KC;
         const bool fast = full16 && (a.Cin - c0) >= KC;
         for (int g = 0; g < tiles; ++g) {
-          const int ab = (na == 2) ? (int)(a_count & 1) : 0;
+          const int ab = (na == 2) ? (int)(a_count_s & 1) : 0;
           const uint32_t a_uses = ab ? a_uses1 : a_uses0;
           uint8_t* Ah = A0 + (size_t)ab * a_bytes;
           const int t_in0 = t_group0 + g * MT - a.pad_left;
@@ -533,7 +432,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_a_full + 8 * ab);
           if (ab) a_uses1 += 1; else a_uses0 += 1;
-          a_count += 1;
+          a_count_s += 1;
         }
       }
     }
@@ -568,7 +467,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
   }
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
