@@ -20,7 +20,10 @@ import sys
 import threading
 import time
 
-import torch
+# NCCL prints its version banner on stdout; the contract is ONE JSON line there, so send NCCL's log to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
