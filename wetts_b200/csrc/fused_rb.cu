@@ -10,7 +10,7 @@
 namespace wetts {
 namespace {
 
-// dst[tap][kh][hi|lo][kg][n][e] <- folded weight src[co][ci][tap] (3xTF32 split)
+// dst[tap][32-channel slice][k-group][hi|lo][n][e] <- folded weight src[co][ci][tap] (3xTF32 split; fused_rb_pack_index)
 __global__ void fused_rb_pack_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int K) {
   const long long total = (long long)K * C * C * 2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -72,12 +72,9 @@ void launch_fused_rb_pack(const float* w_folded, float* dst, int C, int K, cudaS
 
 template <int C, int THREADS, int MINB, int NB, bool PROFILE>
 static int launch_variant(const FusedRbArgs& a, int grid, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;
   auto kern = fused_resblock2_kernel<C, THREADS, MINB, NB, PROFILE>;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
-    configured = smem;
-  }
+  // per launch (not cached): the attribute is per device and costs microseconds
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
   kern<<<grid, THREADS, smem, s>>>(a);
   count_launch();
   return 0;
@@ -125,12 +122,9 @@ int launch_fused_rb(int C, FusedRbArgs a, cudaStream_t s) {
   if ((a.T & 3) != 0 || (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.w) & 15) != 0) return 1;   // 16 B loads / bulk copies
   fused_rb_finalize_args(a, C);
   if (dyn_smem_offset(&a.smem_off, s)) return 1;
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  }
+  int n_sm = 0, dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) return 1;
   const char* force = getenv("WETTS_FUSED_RB_RING");
   const int ring = force ? atoi(force) : fused_rb_ring_slots(a.nq);
   if (ring != 4 && !(ring == 6 && a.nq % 6 == 0)) return 1;
