@@ -628,8 +628,8 @@ int wetts_vits_finalize(wetts_vits_t h) {
               off += fused_rb_conv_floats(ch, cv.K);
             }
           h->fused_rb_w.back() = fw;
-          uint32_t off = 0;   // probe the dynamic shared-memory base now, not inside the first timed call
-          if (dyn_smem_offset(&off, 0)) return fail("dynamic shared memory probe failed");
+          uint32_t smem_base = 0;   // probe the dynamic shared-memory base now, not inside the first timed call
+          if (dyn_smem_offset(&smem_base, 0)) return fail("dynamic shared memory probe failed");
         }
       }
     }
