@@ -20,6 +20,7 @@
 //   and keeps the weight tile resident when it can.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "epilogue.cuh"
 #include "kernels.cuh"
@@ -535,11 +536,16 @@ bool tc_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
       }
   }
   // ---- large mode (N a multiple of 64 so that 16 warps split the columns in 16-wide pieces); prefer the
-  // widest N tile, fall back to narrower tiles when the weight tile of one tap does not fit
+  // widest N tile, fall back to narrower tiles when the weight tile of one tap does not fit.
+  // WETTS_TC_PLAN_VARIANT (experiments): bit 0 = try one 128-row block per tile first (smaller activation
+  // buffers -> larger K chunks, more tiles per weight pass); bit 1 = cap the N tile at 128 columns.
+  static const int variant = getenv("WETTS_TC_PLAN_VARIANT") ? atoi(getenv("WETTS_TC_PLAN_VARIANT")) : 0;
   const int cout64 = (Cout + 63) / 64 * 64;
-  for (int n_tiles = (cout64 + 255) / 256; n_tiles <= cout64 / 64; ++n_tiles) {
+  const int nt0 = (variant & 2) ? (cout64 + 127) / 128 : (cout64 + 255) / 256;
+  for (int n_tiles = nt0; n_tiles <= cout64 / 64; ++n_tiles) {
     const int N = ((cout64 + n_tiles - 1) / n_tiles + 63) / 64 * 64;
-    for (int MB = 2; MB >= 1; --MB) {
+    for (int mbi = 0; mbi < 2; ++mbi) {
+      const int MB = (variant & 1) ? 1 + mbi : 2 - mbi;
       if (MB * N > 512) continue;
       for (int nch = 1; nch <= cin8 / 8; ++nch) {
         const int KC = ((cin8 + nch - 1) / nch + 7) / 8 * 8;
