@@ -20,7 +20,7 @@ struct FusedRbArgs {
   const float* bias2[3] = {nullptr, nullptr, nullptr};
   int B = 0, T = 0, nrb = 0;
   int k[3] = {0, 0, 0}, d1[3] = {0, 0, 0}, d2[3] = {0, 0, 0};
-  int Rp = 0;                  // row pitch of a channel group in the activation buffer: >= 128 + 2*max_j Hp_j, odd
+  int Rp = 0;                  // row pitch of a channel group in the activation buffer (= kFusedRbPitch; informational)
   int nq = 0;                  // weight chunks per item = sum_j 2*k_j*(C/32)
   int nq_ring = 0;             // nq / ring slots when the ring size divides nq (6-slot ring), else 0
   int qoff[6] = {0, 0, 0, 0, 0, 0};  // first chunk (within the item) of conv 2*j + {0: conv1, 1: conv2}
@@ -42,22 +42,17 @@ inline int fused_rb_ring_slots(int nq) { return (nq % 6 == 0) ? 6 : 4; }
 inline size_t fused_rb_smem_bytes(int C, int ring, int Rp = kFusedRbPitch) {
   return 128 + (size_t)ring * fused_rb_chunk_floats(C) * 4 + 6 * (size_t)C * 4 + 2 * (size_t)C * Rp * 4;
 }
-// Derived launch fields (Rp, nq, qoff) from (nrb, k, d1, d2).
+// Derived launch fields (nq, qoff, nq_ring, Rp) from (nrb, k).
 inline void fused_rb_finalize_args(FusedRbArgs& a, int C) {
-  int Hmax = 0;
   a.nq = 0;
   for (int j = 0; j < a.nrb; ++j) {
-    const int H = (a.d1[j] + a.d2[j]) * (a.k[j] - 1) / 2;
-    const int Hp = (H + 3) & ~3;
-    if (Hp > Hmax) Hmax = Hp;
     a.qoff[2 * j] = a.nq;
     a.nq += a.k[j] * (C / 32);
     a.qoff[2 * j + 1] = a.nq;
     a.nq += a.k[j] * (C / 32);
   }
   a.nq_ring = (a.nq % 6 == 0) ? a.nq / 6 : 0;
-  a.Rp = kFusedRbPitch;   // compile-time pitch; fused_rb_supported() guarantees 128 + 2*Hmax <= pitch
-  (void)Hmax;
+  a.Rp = kFusedRbPitch;   // compile-time pitch; fused_rb_supported() guarantees 128 + 2*Hp_max <= pitch
 }
 
 // Packed weight element i of a conv [C][C][k] (chunk order: tap, 32-channel slice): returns the source

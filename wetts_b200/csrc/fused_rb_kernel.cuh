@@ -26,9 +26,9 @@
 // fp32 accuracy: 3xTF32 in the two-MMA form of tc_mma_tf32_split2 (weights stored [hi | lo] along N; the
 // accumulator of a block is [hi*hi | hi*lo + lo*hi], summed in the epilogue).
 //
-// Weights stream through a 4-slot shared-memory ring of 32-input-channel chunks (one tap, hi+lo,
-// C/32 chunks per tap) fetched by cp.async.bulk three chunks ahead of the MMAs; the chunk sequence is
-// identical for every item so the ring never drains between items.  Warp 0 only issues MMAs (the tensor
+// Weights stream through a 4- or 6-slot shared-memory ring of 32-input-channel chunks (one tap, hi+lo,
+// C/32 chunks per tap): a slot is refilled by cp.async.bulk (L2 evict_last) the moment the MMAs that read it
+// complete; the chunk sequence is identical for every item so the ring never drains between items.  Warp 0 only issues MMAs (the tensor
 // pipe's instruction queue is shallow, so every cycle the issuer spends elsewhere is a pipe bubble); warp 1
 // runs the weight producer during the MMA phases.  The next tile's activations are prefetched into registers
 // (16 B loads, 4 rows x 4 channels per unit) while the tensor pipe works.
