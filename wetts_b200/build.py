@@ -56,5 +56,28 @@ def build(force=False, verbose=False):
     return LIB
 
 
+RUNTIME = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "runtime")
+RUNTIME_BIN = os.path.join(RUNTIME, "vits_main")
+
+
+def build_runtime(force=False):
+    """C++ `VitsModel` shim + CLI (runtime/): host code only (g++), linked against libwetts_b200.so and cudart."""
+    srcs = [os.path.join(RUNTIME, f) for f in ("vits_model.cc", "vits_main.cc")]
+    deps = srcs + [os.path.join(RUNTIME, "vits_model.h"), LIB]
+    if not force and os.path.exists(RUNTIME_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(RUNTIME_BIN) for d in deps):
+        return RUNTIME_BIN
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    inc = os.path.join(os.path.dirname(RUNTIME), "include")
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I", inc, "-I", RUNTIME, "-I", os.path.join(cuda, "include")] + srcs + [
+        "-o", RUNTIME_BIN, "-L", CSRC, "-lwetts_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart",
+        "-Wl,-rpath," + CSRC, "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("runtime build failed")
+    return RUNTIME_BIN
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_runtime(force="--force" in sys.argv))
