@@ -176,6 +176,15 @@ size_t wetts_vits_decoder_workspace_bytes(wetts_vits_t h, int B, int L);
 int wetts_vits_forward_decoder(wetts_vits_t h, const float* z_blc, const int64_t* sid, int B, int L, float* audio,
                                void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- output stage of the callers ---------------------------------
+ * audio f32[B,L] in [-1,1] -> int16[B,L] on the device.  mode 0: x32767 (cli/model.py:60, vits_model.cc:84-86);
+ * mode 1: per utterance 32767 / max(0.01, max|a|) * 0.6 (inference.py:101-105), the peak searched over the first
+ * lengths[b] samples when `lengths` (int64[B]) is given; mode 2: one such gain for the whole batch
+ * (runtime/gpu_triton model.py:150-151).  Values are clipped to +-32767 and truncated toward zero like
+ * numpy's astype(int16).  peak_scratch: device float[B] (modes 1, 2; may be NULL for mode 0). */
+int wetts_audio_to_int16(const float* audio, const int64_t* lengths, int B, int64_t L, int mode, float* peak_scratch,
+                         int16_t* out, void* stream);
+
 /* Counters for benchmarks: number of kernels this library has launched on behalf
  * of the handle since creation (monotonic). */
 uint64_t wetts_vits_launch_count(wetts_vits_t h);

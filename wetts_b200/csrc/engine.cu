@@ -418,6 +418,17 @@ int wetts_get_option(const char* name, int* value) {
   }
   return fail("unknown option '%s'", name);
 }
+int wetts_audio_to_int16(const float* audio, const int64_t* lengths, int B, int64_t L, int mode, float* peak_scratch,
+                         int16_t* out, void* stream) {
+  if (!audio || !out || B <= 0 || L <= 0) return fail("wetts_audio_to_int16: empty input");
+  if (mode < 0 || mode > 2) return fail("wetts_audio_to_int16: unknown mode %d", mode);
+  if (mode != 0 && !peak_scratch) return fail("wetts_audio_to_int16: the peak modes need a float[B] scratch buffer");
+  launch_audio_to_int16(audio, (const long long*)lengths, B, (long long)L, mode, peak_scratch, (short*)out,
+                        (cudaStream_t)stream);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 uint64_t wetts_vits_launch_count(wetts_vits_t h) { return h ? kernel_launch_counter() - h->launches_at_create : 0; }
 
 int wetts_vits_set_tensor(wetts_vits_t h, const char* name, const void* data, const int64_t* dims, int ndim) {

@@ -171,6 +171,9 @@ void launch_expand_prior(const float* m, const float* logs, const int* cum, cons
 void launch_max_i64(const long long* v, int n, long long* out, cudaStream_t s);
 // [B][L][C] -> [B][C][L]
 void launch_transpose_blc(const float* in, float* out, int B, int L, int C, cudaStream_t s);
+// callers' output stage: mode 0 x32767, 1 per-utterance peak * 0.6, 2 batch-global peak * 0.6; clip, truncate to int16
+void launch_audio_to_int16(const float* audio, const long long* lengths, int B, long long L, int mode, float* peak,
+                           short* out, cudaStream_t s);
 
 unsigned long long kernel_launch_counter();
 void count_launch();

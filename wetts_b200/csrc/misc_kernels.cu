@@ -666,6 +666,54 @@ void launch_max_i64(const long long* v, int n, long long* out, cudaStream_t s) {
   max_i64_kernel<<<1, 256, 0, s>>>(v, n, out);
   count_launch();
 }
+// ------------------------------------------------------------------ output stage (callers' int16 conversion)
+// peak[b] (or peak[0] for the batch-global mode) = max |audio| over the valid samples; non-negative floats order
+// like their bit patterns, so the reduction is an integer atomicMax.
+__global__ void __launch_bounds__(256) audio_peak_kernel(const float* __restrict__ audio, const long long* __restrict__ lengths,
+                                                         long long L, int global_peak, float* __restrict__ peak) {
+  const int b = blockIdx.y;
+  const long long n = lengths ? (lengths[b] < L ? lengths[b] : L) : L;
+  const float* row = audio + (long long)b * L;
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(row[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float wm[8];
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    m = wm[threadIdx.x];
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffu, m, o));
+    if (threadIdx.x == 0) atomicMax(reinterpret_cast<int*>(peak + (global_peak ? 0 : b)), __float_as_int(m));
+  }
+}
+// out = int16(trunc(clip(audio * gain, +-32767))); gain = 32767 (mode 0) or 32767 / max(0.01, peak) * 0.6
+// (inference.py:101-105: the same fp32 operation order)
+__global__ void __launch_bounds__(256) audio_to_int16_kernel(const float* __restrict__ audio, const float* __restrict__ peak,
+                                                             long long L, int mode, short* __restrict__ out) {
+  const int b = blockIdx.y;
+  float g = 32767.0f;
+  if (mode != 0) g = 32767.0f / fmaxf(peak[mode == 2 ? 0 : b], 0.01f) * 0.6f;
+  const float* row = audio + (long long)b * L;
+  short* orow = out + (long long)b * L;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < L; i += (long long)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(row[i] * g, -32767.0f), 32767.0f);
+    orow[i] = (short)__float2int_rz(v);
+  }
+}
+void launch_audio_to_int16(const float* audio, const long long* lengths, int B, long long L, int mode, float* peak,
+                           short* out, cudaStream_t s) {
+  const int gx = (int)((L + 256 * 8 - 1) / (256 * 8) > 1024 ? 1024 : (L + 256 * 8 - 1) / (256 * 8));
+  dim3 grid(gx < 1 ? 1 : gx, B);
+  if (mode != 0) {
+    cudaMemsetAsync(peak, 0, sizeof(float) * (mode == 2 ? 1 : B), s);
+    audio_peak_kernel<<<grid, 256, 0, s>>>(audio, lengths, L, mode == 2, peak);
+    count_launch();
+  }
+  audio_to_int16_kernel<<<grid, 256, 0, s>>>(audio, peak, L, mode, out);
+  count_launch();
+}
+
 void launch_transpose_blc(const float* in, float* out, int B, int L, int C, cudaStream_t s) {
   dim3 grid((L + 31) / 32, (C + 31) / 32, B);
   transpose_blc_kernel<<<grid, dim3(32, 8), 0, s>>>(in, out, L, C);

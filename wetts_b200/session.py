@@ -111,21 +111,25 @@ class StreamingVits:
 
 
 def to_int16(audio, mode="scale", lengths=None):
-    """audio f32[B,1,L] or [B,L] in [-1,1] -> int16 (same shape), on the audio's device.
-    mode "scale": x32767; "peak": per utterance 32767/max(0.01, max|a|)*0.6 then clip;
-    "peak_batch": one gain for the whole batch.  `lengths` (valid samples per row) restricts the
-    peak search of "peak" to each utterance's own samples."""
-    a = audio.float()
-    if mode == "scale":
-        g = a.new_tensor(32767.0)
-    elif mode == "peak_batch":
-        g = 32767.0 / a.abs().max().clamp_min(0.01) * 0.6
-    elif mode == "peak":
-        flat = a.reshape(a.shape[0], -1)
-        if lengths is not None:
-            valid = torch.arange(flat.shape[1], device=a.device)[None, :] < lengths.to(a.device)[:, None]
-            flat = flat * valid
-        g = (32767.0 / flat.abs().amax(dim=1).clamp_min(0.01) * 0.6).reshape([-1] + [1] * (a.dim() - 1))
-    else:
+    """audio f32[B,1,L] or [B,L] in [-1,1] -> int16 (same shape), on the audio's device (one CUDA kernel pair behind
+    `wetts_audio_to_int16`, no CPU path).  mode "scale": x32767; "peak": per utterance
+    32767/max(0.01, max|a|)*0.6 then clip; "peak_batch": one gain for the whole batch.  `lengths` (valid samples
+    per row) restricts the peak search of "peak" to each utterance's own samples."""
+    from . import _lib
+    from ._lib import WettsError, check
+    modes = {"scale": 0, "peak": 1, "peak_batch": 2}
+    if mode not in modes:
         raise ValueError(mode)
-    return (a * g).clamp(-32767.0, 32767.0).to(torch.int16)
+    if not (torch.is_tensor(audio) and audio.is_cuda):
+        raise WettsError("to_int16 runs on CUDA tensors only (wetts_b200 has no CPU fallback)")
+    a = audio.float().contiguous()
+    B = a.shape[0]
+    L = a.numel() // B
+    out = torch.empty(a.shape, dtype=torch.int16, device=a.device)
+    scratch = torch.empty(max(B, 1), dtype=torch.float32, device=a.device)
+    ln = None if lengths is None else lengths.to(device=a.device, dtype=torch.int64).contiguous()
+    with torch.cuda.device(a.device):
+        st = torch.cuda.current_stream(a.device).cuda_stream
+        check(_lib.load().wetts_audio_to_int16(a.data_ptr(), None if ln is None else ln.data_ptr(), B, L, modes[mode],
+                                               scratch.data_ptr(), out.data_ptr(), st))
+    return out
