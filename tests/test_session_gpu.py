@@ -94,43 +94,6 @@ def test_int16_output_stage():
     assert abs(int(b[0, 0, 0]) - int(32767 * 0.6)) <= 1 and abs(int(b[1, 0, 2])) < 3000
 
 
-def test_int16_output_stage_matches_the_callers_formulas():
-    """wetts_audio_to_int16 against the three caller formulas (inference.py:101-105 per utterance, gpu_triton
-    model.py:150-151 batch-global, cli/model.py:60 plain scale).  Plain scale: exact.  Peak modes: the kernel
-    evaluates 32767 / max(0.01, peak) * 0.6 in fp32 in the reference's operation order; a torch re-evaluation may
-    round the gain one ulp differently (e.g. `scalar / tensor` is reciprocal-times-scalar in torch), which moves a
-    truncated int16 sample by at most one step."""
-    gen = torch.Generator().manual_seed(3)
-    a = (torch.randn(5, 1, 4099, generator=gen) * torch.tensor([0.3, 0.02, 1.7, 0.004, 0.9])[:, None, None]).cuda()
-    lens = torch.tensor([4099, 1000, 37, 4099, 2048])
-
-    def ref(mode):
-        x = a.float()
-        full = x.new_tensor(32767.0)
-        if mode == "scale":
-            g = full
-        elif mode == "peak_batch":
-            g = torch.div(full, x.abs().max().clamp_min(0.01)) * 0.6
-        else:
-            flat = x.reshape(5, -1) * (torch.arange(4099, device="cuda")[None, :] < lens.cuda()[:, None])
-            g = (torch.div(full, flat.abs().amax(dim=1).clamp_min(0.01)) * 0.6).reshape(5, 1, 1)
-        return (x * g).clamp(-32767.0, 32767.0).to(torch.int16)
-
-    assert torch.equal(to_int16(a, "scale"), ref("scale"))
-    for mode, kw in (("peak_batch", {}), ("peak", {"lengths": lens})):
-        got, want = to_int16(a, mode, **kw), ref(mode)
-        assert got.dtype == torch.int16 and got.shape == want.shape
-        assert int((got.int() - want.int()).abs().max()) <= 1
-    # per-utterance gain: the loudest valid sample of every row lands on 0.6 full scale (or clips when the peak
-    # lies outside the valid prefix)
-    p = to_int16(a, "peak", lengths=lens).int().reshape(5, -1)
-    for b in range(5):
-        assert abs(int(p[b, : int(lens[b])].abs().max()) - int(32767 * 0.6)) <= 2
-    assert to_int16(a[:, 0], "scale").shape == (5, 4099)
-    with pytest.raises(wetts_b200.WettsError):
-        to_int16(a.cpu(), "scale")
-
-
 def test_tensor_core_and_simt_paths_agree():
     """Same inputs through the tcgen05 3xTF32 path and the fp32 SIMT path."""
     hps, sd, g, t = load_case("v3_ragged")
@@ -185,3 +148,40 @@ def test_c_abi_error_reporting(v3):
     bad.load_state_dict(sd)
     with pytest.raises(wetts_b200.WettsError, match="dec.conv_post.weight"):
         bad.to("cuda")
+
+
+def test_int16_output_stage_matches_the_callers_formulas():
+    """wetts_audio_to_int16 against the three caller formulas (inference.py:101-105 per utterance, gpu_triton
+    model.py:150-151 batch-global, cli/model.py:60 plain scale).  Plain scale: exact.  Peak modes: the kernel
+    evaluates 32767 / max(0.01, peak) * 0.6 in fp32 in the reference's operation order; a torch re-evaluation may
+    round the gain one ulp differently (e.g. `scalar / tensor` is reciprocal-times-scalar in torch), which moves a
+    truncated int16 sample by at most one step."""
+    gen = torch.Generator().manual_seed(3)
+    a = (torch.randn(5, 1, 4099, generator=gen) * torch.tensor([0.3, 0.02, 1.7, 0.004, 0.9])[:, None, None]).cuda()
+    lens = torch.tensor([4099, 1000, 37, 4099, 2048])
+
+    def ref(mode):
+        x = a.float()
+        full = x.new_tensor(32767.0)
+        if mode == "scale":
+            g = full
+        elif mode == "peak_batch":
+            g = torch.div(full, x.abs().max().clamp_min(0.01)) * 0.6
+        else:
+            flat = x.reshape(5, -1) * (torch.arange(4099, device="cuda")[None, :] < lens.cuda()[:, None])
+            g = (torch.div(full, flat.abs().amax(dim=1).clamp_min(0.01)) * 0.6).reshape(5, 1, 1)
+        return (x * g).clamp(-32767.0, 32767.0).to(torch.int16)
+
+    assert torch.equal(to_int16(a, "scale"), ref("scale"))
+    for mode, kw in (("peak_batch", {}), ("peak", {"lengths": lens})):
+        got, want = to_int16(a, mode, **kw), ref(mode)
+        assert got.dtype == torch.int16 and got.shape == want.shape
+        assert int((got.int() - want.int()).abs().max()) <= 1
+    # per-utterance gain: the loudest valid sample of every row lands on 0.6 full scale (or clips when the peak
+    # lies outside the valid prefix)
+    p = to_int16(a, "peak", lengths=lens).int().reshape(5, -1)
+    for b in range(5):
+        assert abs(int(p[b, : int(lens[b])].abs().max()) - int(32767 * 0.6)) <= 2
+    assert to_int16(a[:, 0], "scale").shape == (5, 4099)
+    with pytest.raises(wetts_b200.WettsError):
+        to_int16(a.cpu(), "scale")
