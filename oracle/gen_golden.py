@@ -28,7 +28,16 @@ CASES = [
     ("v3_single", "multilingual_v3", 256, 2, [7], (0.667, 4.0, 0.8), 5679),
     ("v1_ragged", "baker_v1", 256, 1, [10, 6], (0.667, 3.0, 0.8), 5680),
     ("v2_short", "baker_v2", 256, 1, [3, 4], (0.667, 3.0, 0.8), 5681),
+    # BASELINE.json configs[4] family: AISHELL-3 v1 (44.1 kHz, 218 speakers, SDP, HiFi-GAN V1), longer ragged text
+    ("aishell3_long", "aishell3_v1", 256, 218, [128, 80], (0.667, 2.0, 0.8), 5682),
+    # BASELINE.json configs[0]: Baker v1, batch 1, the CLI utterance, CLI scales
+    ("baker_v1_cli", "baker_v1", None, 1, "cli", (0.667, 1.0, 0.8), 5683),
 ]
+
+# phoneme string of the wetts.cli example utterance and the synthetic phones.txt rule
+# (`sil 0`, then the sorted remaining symbols; examples/baker/run.sh:38-41)
+CLI_TOKENS = "sil j in1 #0 t ian1 #0 t ian1 #0 q i4 #0 z en3 #0 m e5 #0 ^ iang4 #4".split()
+CLI_VOCAB = ["sil"] + sorted(set(CLI_TOKENS) - {"sil"})
 
 
 def make_inputs(n_vocab, n_speakers, x_lengths, seed, max_frames_per_phone=40):
@@ -46,11 +55,21 @@ def make_inputs(n_vocab, n_speakers, x_lengths, seed, max_frames_per_phone=40):
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(1)
+    only = set(sys.argv[1:])
     for name, cfg_name, n_vocab, n_spk, x_lengths, scales, seed in CASES:
+        if only and name not in only:
+            continue
         hps = builtin_config(cfg_name)
+        cli_ids = None
+        if x_lengths == "cli":
+            n_vocab = len(CLI_VOCAB)
+            cli_ids = [CLI_VOCAB.index(t) for t in CLI_TOKENS]
+            x_lengths = [len(cli_ids)]
         sd = synth.make_state_dict(hps.model, n_vocab, n_spk, seed=hps.train.seed)
         net = ref_harness.build_reference_model(hps, n_vocab, n_spk, sd)
         x, lens, sid, noise_w, noise_z = make_inputs(n_vocab, n_spk, x_lengths, seed)
+        if cli_ids is not None:
+            x = torch.tensor([cli_ids], dtype=torch.long)
         ns, ls, nsw = scales
         r = ref_harness.reference_infer(net, x, lens, sid, ns, ls, nsw, noise_w, noise_z)
         Ty = r["z"].shape[2]

@@ -4,12 +4,12 @@ import pytest
 import torch
 
 from oracle import vits_oracle as O
-from tests.golden_util import CASES, load_case, rel_rms_err
+from tests.golden_util import CASES, WIDE_CASES, load_case, rel_rms_err
 
 TOL = 2e-5  # relative to rms; both sides are fp32 CPU, differences are summation order only
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + WIDE_CASES)
 def test_oracle_matches_reference_fixture(name):
     hps, sd, g, t = load_case(name)
     ns, ls, nsw = [float(v) for v in g["scales"]]
@@ -31,7 +31,7 @@ def test_oracle_matches_reference_fixture(name):
     assert torch.equal(valid.float(), t["attn_rowsum"])
 
 
-@pytest.mark.parametrize("name", ["v3_ragged", "v1_ragged"])
+@pytest.mark.parametrize("name", ["v3_ragged", "v1_ragged", "baker_v1_cli"])
 def test_oracle_own_durations_match_reference(name):
     """Without teacher forcing the oracle's ceil(exp(logw)) lands on the same integers."""
     hps, sd, g, t = load_case(name)

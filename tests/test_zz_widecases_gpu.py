@@ -1,0 +1,48 @@
+"""GPU parity on the two wider reference fixtures (BASELINE.json configs[4] family: AISHELL-3 v1 with 218
+speakers and 128/80-phoneme utterances; configs[0]: Baker v1, the CLI utterance at the CLI's scales).  Same
+checks and tolerances as tests/test_parity_gpu.py; kept in a file that sorts last so that these newer cases run
+after every other GPU test."""
+import pytest
+import torch
+
+from tests.golden_util import WIDE_CASES, load_case, rel_rms_err
+
+pytestmark = pytest.mark.gpu
+
+BLOCK_TOL = 1e-4
+E2E_TOL = 1e-3
+
+
+@pytest.mark.parametrize("name", WIDE_CASES)
+def test_wide_fixture_end_to_end_and_blocks(name):
+    import wetts_b200
+    hps, sd, g, t = load_case(name)
+    net = wetts_b200.build_model(hps, int(g["n_vocab"]), int(g["n_speakers"]), sd, "cuda")
+    dev = net.device
+    ns, ls, nsw = [float(v) for v in g["scales"]]
+    o, attn, y_mask, (z, z_p, m_p, logs_p) = net.infer(
+        t["x"], t["x_lengths"], t["sid"], noise_scale=ns, length_scale=ls, noise_scale_w=nsw,
+        noise_w=t["noise_w"], noise_z=t["noise_z"], durations=t["w_ceil"])
+    torch.cuda.synchronize()
+    assert torch.equal(net.last_y_lengths.cpu(), t["y_lengths"])
+    assert rel_rms_err(z_p.cpu(), t["z_p"]) < BLOCK_TOL
+    assert rel_rms_err(z.cpu(), t["z"]) < BLOCK_TOL * 3
+    assert rel_rms_err(o.cpu(), t["o"]) < E2E_TOL
+    a = attn[:, 0].cpu()
+    valid = t["attn_rowsum"] > 0
+    assert torch.equal(a.sum(-1), t["attn_rowsum"])
+    assert torch.equal(a.argmax(-1)[valid].int(), t["attn_argmax"][valid])
+    # blocks given the reference's intermediates
+    gvec = net.emb_g(t["sid"])[:, :, None] if int(g["n_speakers"]) > 0 else None
+    h, m, logs, x_mask = net.enc_p(t["x"], t["x_lengths"])
+    assert rel_rms_err(h.cpu(), t["h"]) < BLOCK_TOL
+    assert rel_rms_err(m.cpu(), t["m_p_tx"]) < BLOCK_TOL
+    if net.use_sdp:
+        logw = net.dp(t["h"].to(dev), x_mask, g=gvec, reverse=True, noise_scale=nsw, noise=t["noise_w"])
+    else:
+        logw = net.dp(t["h"].to(dev), x_mask, g=gvec)
+    assert rel_rms_err(logw.cpu(), t["logw"]) < 2e-4
+    Ty = t["z"].shape[2]
+    ym = (torch.arange(Ty)[None, :] < t["y_lengths"][:, None]).float()[:, None].to(dev)
+    assert rel_rms_err(net.flow(t["z_p"].to(dev), ym, g=gvec, reverse=True).cpu(), t["z"]) < BLOCK_TOL
+    assert rel_rms_err(net.dec(t["z"].to(dev) * ym, g=gvec).cpu(), t["o"]) < BLOCK_TOL * 3
