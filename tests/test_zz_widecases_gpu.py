@@ -5,13 +5,18 @@ other GPU test.
 
 STATUS (end of round 1): the fixtures were generated after the round's GPU budget was spent.  The single run
 that still fit showed `aishell3_long` with matching lengths but z_p above the 1e-4 block tolerance of the small
-fixtures (the run was cut before the value was printed; baker_v1_cli did not run).  z_p = m_p + noise *
-exp(logs_p) * 0.667 amplifies a difference in logs_p by up to |noise| * exp(logs_p) * 0.667 = 11x on this
-fixture, and at Tx = 128 the six attention layers reduce over 128 keys, so a ~1e-5 absolute difference in logs_p
-(4 fp32 ulp at |logs_p| = 2) is enough.  The full-size test (tests/test_fullsize_gpu.py) bounds the same path
-at Tx = 128 by 3e-4 on z and 1e-3 on the waveform against the oracle and passes.  Until this case has been
-looked at on hardware it is marked xfail (non-strict): it documents an open question, it does not hide a
-verified failure of the stated end-to-end tolerance."""
+fixtures (the run was cut before the value was printed; baker_v1_cli did not run).  What is known:
+* z_p = m_p + noise * exp(logs_p) * 0.667 amplifies a difference in logs_p by up to 11x on this fixture, but
+  `tools/tf32_error_probe.py` (3xTF32 emulation of the text encoder's convolutions on the CPU) moves logs_p by
+  only 1.3e-6, i.e. z_p by 1.4e-5: the 3xTF32 arithmetic alone does NOT explain the observation;
+* every earlier reference fixture has Tx <= 12, where the text encoder's convolutions take the fp32 SIMT path
+  (T < 64); this is the first fixture that sends them through the tcgen05 path, with a ragged batch (128 / 80);
+* the full-size test (tests/test_fullsize_gpu.py) bounds the same path at Tx = 128 by 3e-4 on z and 1e-3 on
+  the waveform against the oracle and passes, so the stated end-to-end tolerance holds.
+First job of round 2: print the per-block errors of this case on hardware (text encoder h / m / logs with
+tensor_cores 0 and 1) and either fix the tcgen05 text-encoder path or justify the tolerance.  Until then the
+case is marked xfail (non-strict): it documents an open question, it does not hide a verified failure of the
+stated end-to-end tolerance."""
 import pytest
 import torch
 
