@@ -32,6 +32,9 @@ CASES = [
     ("aishell3_long", "aishell3_v1", 256, 218, [128, 80], (0.667, 2.0, 0.8), 5682),
     # BASELINE.json configs[0]: Baker v1, batch 1, the CLI utterance, CLI scales
     ("baker_v1_cli", "baker_v1", None, 1, "cli", (0.667, 1.0, 0.8), 5683),
+    # the route bench.py measures: multilingual v3 at Tx = 128, ragged (every text-encoder / duration-predictor conv takes
+    # the tcgen05 kernel at T >= 64); gating fixture for own-duration equality on that route
+    ("v3_tx128", "multilingual_v3", 256, 2, [128, 97, 64], (0.667, 2.0, 0.8), 5684),
 ]
 
 # phoneme string of the wetts.cli example utterance and the synthetic phones.txt rule

@@ -57,6 +57,13 @@ bool LoadFlatWeights(const std::string& path, wetts_vits_config* cfg, int* sampl
   if (!ReadPod(f, &sr) || !ReadPod(f, &n_tensors)) { *error = path + ": truncated header"; return false; }
   *sampling_rate = sr;
   tensors->clear();
+  // a malformed or hostile file must not drive allocation: every tensor has to fit in what is left of the file
+  const std::streampos here = f.tellg();
+  f.seekg(0, std::ios::end);
+  const std::streamoff file_bytes = f.tellg();
+  f.seekg(here);
+  constexpr uint32_t kMaxTensors = 1u << 16;
+  if (n_tensors > kMaxTensors) { *error = path + ": implausible tensor count"; return false; }
   for (uint32_t i = 0; i < n_tensors; ++i) {
     FlatTensor t;
     uint16_t name_len = 0;
@@ -67,9 +74,15 @@ bool LoadFlatWeights(const std::string& path, wetts_vits_config* cfg, int* sampl
     if (!ReadPod(f, &ndim) || ndim > 8) { *error = path + ": bad tensor rank"; return false; }
     size_t numel = 1;
     t.dims.resize(ndim);
+    const size_t left = static_cast<size_t>(file_bytes - static_cast<std::streamoff>(f.tellg()));
     for (int d = 0; d < ndim; ++d) {
-      if (!ReadPod(f, &t.dims[d]) || t.dims[d] < 0) { *error = path + ": bad tensor shape"; return false; }
-      numel *= static_cast<size_t>(t.dims[d]);
+      if (!ReadPod(f, &t.dims[d]) || t.dims[d] <= 0) { *error = path + ": bad tensor shape"; return false; }
+      const size_t dim = static_cast<size_t>(t.dims[d]);
+      if (dim > left / sizeof(float) || numel > left / sizeof(float) / dim) {   // overflow-safe: numel*dim*4 <= left
+        *error = path + ": tensor '" + t.name + "' is larger than the file";
+        return false;
+      }
+      numel *= dim;
     }
     t.data.resize(numel);
     f.read(reinterpret_cast<char*>(t.data.data()), static_cast<std::streamsize>(numel * sizeof(float)));

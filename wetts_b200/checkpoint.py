@@ -11,9 +11,12 @@ import os
 import torch
 
 
-def load_checkpoint(checkpoint_path, model, optimizer=None):
+def load_checkpoint(checkpoint_path, model, optimizer=None, *, trust_pickle=False):
+    """`trust_pickle=True` restores the reference's behaviour (full unpickling, task.py:33) for checkpoints
+    that carry non-tensor objects; the default only materialises tensors and plain containers, so an
+    untrusted .pth cannot execute code."""
     assert os.path.isfile(checkpoint_path), checkpoint_path
-    ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+    ckpt = torch.load(checkpoint_path, map_location="cpu", weights_only=not trust_pickle)
     state = ckpt["model"] if isinstance(ckpt, dict) and "model" in ckpt else ckpt
     model.load_state_dict(state)
     return model, optimizer, ckpt.get("learning_rate", None), ckpt.get("iteration", 0)

@@ -8,16 +8,55 @@
 // wavefront for any dilation, and weight reads are warp-uniform float4 broadcasts.
 // Epilogues fuse bias, residual adds, the MRF mean, the WaveNet gate, the res/skip
 // split and the coupling update, so no elementwise kernel touches HBM in between.
+#include <atomic>
 #include <cstdio>
+#include <mutex>
 
 #include "kernels.cuh"
 #include "epilogue.cuh"
 
 namespace wetts {
 
-static unsigned long long g_launch_count = 0;
-unsigned long long kernel_launch_counter() { return g_launch_count; }
-void count_launch() { ++g_launch_count; }
+static std::atomic<unsigned long long> g_launch_count{0};
+unsigned long long kernel_launch_counter() { return g_launch_count.load(std::memory_order_relaxed); }
+void count_launch() { g_launch_count.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local cudaError_t g_launcher_error = cudaSuccess;
+void note_launcher_error(cudaError_t e) { if (e != cudaSuccess && g_launcher_error == cudaSuccess) g_launcher_error = e; }
+cudaError_t take_launcher_error() { cudaError_t e = g_launcher_error; g_launcher_error = cudaSuccess; return e; }
+
+cudaError_t DynSmemAttr::ensure(const void* func, size_t bytes) {
+  static std::mutex mu_all;   // growth is rare (a handful of times per process): one lock for every launch site
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { note_launcher_error(e); return e; }
+  if (dev < 0 || dev >= kMaxDev) {   // uncached device index: set it every time
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    note_launcher_error(e);
+    return e;
+  }
+  if (bytes <= __atomic_load_n(&have[dev], __ATOMIC_ACQUIRE)) return cudaSuccess;
+  std::lock_guard<std::mutex> lock(mu_all);
+  if (bytes <= have[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) __atomic_store_n(&have[dev], bytes, __ATOMIC_RELEASE);
+  note_launcher_error(e);
+  return e;
+}
+
+int current_device_sm_count() {
+  static std::atomic<int> cache[DynSmemAttr::kMaxDev];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < DynSmemAttr::kMaxDev) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (dev >= 0 && dev < DynSmemAttr::kMaxDev) cache[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
 
 namespace {
 
@@ -147,11 +186,8 @@ void launch_conv_inst(const ConvArgs& a, cudaStream_t s) {
   constexpr int T_TILE = 32 * TN * WARPS_T;
   const int XS = T_TILE + (a.K - 1) * a.dil;
   const size_t smem = sizeof(float) * ((size_t)kCiChunk * XS + (size_t)kCiChunk * a.K * CO_TILE);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(conv1d_kernel<TN, WARPS_CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static DynSmemAttr attr;
+  if (attr.ensure((const void*)conv1d_kernel<TN, WARPS_CO>, smem) != cudaSuccess) return;
   dim3 grid((a.T + T_TILE - 1) / T_TILE, a.CoutPad / CO_TILE, a.B);
   conv1d_kernel<TN, WARPS_CO><<<grid, kThreads, smem, s>>>(a);
   count_launch();
@@ -256,11 +292,8 @@ void launch_convT_inst(const ConvTArgs& a, cudaStream_t s) {
   constexpr int N_TILE = 32 * TN * WARPS_T;
   const int QN = N_TILE / a.u + a.ntaps;
   const size_t smem = sizeof(float) * ((size_t)kCiChunkT * a.ntaps * CO_TILE * a.u + (size_t)kCiChunkT * QN);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(convT_kernel<TN, WARPS_CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static DynSmemAttr attr;
+  if (attr.ensure((const void*)convT_kernel<TN, WARPS_CO>, smem) != cudaSuccess) return;
   dim3 grid((a.T * a.u + N_TILE - 1) / N_TILE, a.CoutPad / CO_TILE, a.B);
   convT_kernel<TN, WARPS_CO><<<grid, kThreads, smem, s>>>(a);
   count_launch();
@@ -432,11 +465,8 @@ void launch_conv_post_tanh(const float* in, const float* w, float* out, int B, i
     return;
   }
   const size_t smem = sizeof(float) * ((size_t)kPostCi * (kPostTile + K - 1) + (size_t)C * K);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(conv_post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static DynSmemAttr attr;
+  if (attr.ensure((const void*)conv_post_kernel, smem) != cudaSuccess) return;
   dim3 grid((T + kPostTile - 1) / kPostTile, B);
   conv_post_kernel<<<grid, kThreads, smem, s>>>(in, w, out, C, T, K, slope);
   count_launch();

@@ -665,7 +665,12 @@ int wetts_vits_finalize(wetts_vits_t h) {
   if (!(h)->finalized) return fail("handle not finalized"); \
   CUDA_OK(cudaSetDevice((h)->device));
 
-#define CHECK_LAUNCH() CUDA_OK(cudaGetLastError())
+#define CHECK_LAUNCH()                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _le = take_launcher_error();                                                             \
+    if (_le != cudaSuccess) return fail("kernel attribute setup failed: %s", cudaGetErrorString(_le)); \
+    CUDA_OK(cudaGetLastError());                                                                         \
+  } while (0)
 
 // ------------------------------------------------------------------ speaker embedding
 int wetts_speaker_embedding(wetts_vits_t h, const int64_t* sid, int B, float* g, void* stream) {

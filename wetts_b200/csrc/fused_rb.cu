@@ -1,7 +1,9 @@
 // Launch side of the fused ResBlock2/MRF stage kernel (fused_rb_kernel.cuh): weight packing into the
 // per-item chunk sequence, eligibility checks, persistent-grid launch.
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 #include "fused_rb_kernel.cuh"
@@ -30,7 +32,17 @@ __global__ void probe_dyn_smem_kernel(uint32_t* out) {
 }  // namespace
 
 int dyn_smem_offset(uint32_t* off, cudaStream_t s) {
-  static int cached = -1;
+  // per device (the window offset is a property of the device / driver); racing first calls probe twice, harmlessly
+  static std::atomic<int> cache[DynSmemAttr::kMaxDev];
+  static std::atomic<bool> init{false};
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!init.load()) { for (auto& c : cache) c.store(-1); init.store(true); }
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= DynSmemAttr::kMaxDev) return 1;
+  int cached = cache[dev].load();
   if (cached < 0) {
     uint32_t* d = nullptr;
     uint32_t h = 0;
@@ -40,6 +52,7 @@ int dyn_smem_offset(uint32_t* off, cudaStream_t s) {
     if (cudaStreamSynchronize(s) != cudaSuccess) return 1;
     cudaFree(d);
     cached = (int)h;
+    cache[dev].store(cached);
   }
   *off = (uint32_t)cached;
   return 0;
@@ -122,9 +135,8 @@ int launch_fused_rb(int C, FusedRbArgs a, cudaStream_t s) {
   if ((a.T & 3) != 0 || (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.w) & 15) != 0) return 1;   // 16 B loads / bulk copies
   fused_rb_finalize_args(a, C);
   if (dyn_smem_offset(&a.smem_off, s)) return 1;
-  int n_sm = 0, dev = 0;
-  cudaGetDevice(&dev);
-  if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) return 1;
+  const int n_sm = current_device_sm_count();
+  if (n_sm <= 0) return 1;
   const char* force = getenv("WETTS_FUSED_RB_RING");
   const int ring = force ? atoi(force) : fused_rb_ring_slots(a.nq);
   if (ring != 4 && !(ring == 6 && a.nq % 6 == 0)) return 1;

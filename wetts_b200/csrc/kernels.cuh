@@ -178,4 +178,18 @@ void launch_audio_to_int16(const float* audio, const long long* lengths, int B, 
 unsigned long long kernel_launch_counter();
 void count_launch();
 
+// Per-DEVICE cache of cudaFuncAttributeMaxDynamicSharedMemorySize (the attribute is per device and per function;
+// a process may drive several GPUs and several host threads).  One static instance per launch site / kernel
+// instantiation.  ensure() is thread-safe (double-checked under a mutex) and returns the CUDA error, if any.
+struct DynSmemAttr {
+  static constexpr int kMaxDev = 64;
+  size_t have[kMaxDev] = {};
+  cudaError_t ensure(const void* func, size_t bytes);
+};
+// SM count of the current device (cached per device)
+int current_device_sm_count();
+// last launcher-side error (cudaFuncSetAttribute failures etc.); cleared when read
+cudaError_t take_launcher_error();
+void note_launcher_error(cudaError_t e);
+
 }  // namespace wetts

@@ -617,11 +617,8 @@ void launch_rel_attention(const float* qkv, const float* emb_k, const float* emb
   const int dk = C / n_heads;
   const int Tpad = (T + 3) & ~3;
   const size_t smem = sizeof(float) * ((size_t)dk * kAttQ * 2 + (size_t)dk * (kAttKT + 1) + (size_t)kAttQ * Tpad);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(rel_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static DynSmemAttr attr;
+  if (attr.ensure((const void*)rel_attention_kernel, smem) != cudaSuccess) return;
   dim3 grid((T + kAttQ - 1) / kAttQ, n_heads, B);
   rel_attention_kernel<<<grid, kAttThreads, smem, s>>>(qkv, emb_k, emb_v, lengths, out, C, T, n_heads, window, dk, Tpad);
   count_launch();

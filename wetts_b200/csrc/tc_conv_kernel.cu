@@ -585,27 +585,17 @@ void launch_conv1d_tc(const ConvArgs& a, cudaStream_t s) {
   p.tmem_cols = pl.tmem_cols; p.G = pl.tmem_cols / (MB * pl.N);
   p.n_abuf = pl.n_abuf; p.n_bbuf = pl.n_bbuf; p.R_pad = (R + 7) & ~7;
   const size_t smem = tc_conv_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, pl.n_abuf, pl.n_bbuf);
-  static size_t configured[2] = {0, 0};
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  }
+  static DynSmemAttr attr[2];
+  const int n_sm = current_device_sm_count();
+  if (n_sm <= 0) return;
   const int group_rows = p.G * 128 * MB;
   const long long items = (long long)a.B * ((a.T + group_rows - 1) / group_rows) * pl.n_tiles;
   if (pl.mode == 0) {
-    if (smem > configured[0]) {
-      cudaFuncSetAttribute(conv1d_tc_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured[0] = smem;
-    }
+    if (attr[0].ensure((const void*)conv1d_tc_kernel<256, 2>, smem) != cudaSuccess) return;
     const int grid = (int)(items < 2 * n_sm ? items : 2 * n_sm);
     conv1d_tc_kernel<256, 2><<<grid, 256, smem, s>>>(p);
   } else {
-    if (smem > configured[1]) {
-      cudaFuncSetAttribute(conv1d_tc_kernel<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      configured[1] = smem;
-    }
+    if (attr[1].ensure((const void*)conv1d_tc_kernel<512, 1>, smem) != cudaSuccess) return;
     const int grid = (int)(items < n_sm ? items : n_sm);
     conv1d_tc_kernel<512, 1><<<grid, 512, smem, s>>>(p);
   }

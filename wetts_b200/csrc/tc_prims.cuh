@@ -127,6 +127,25 @@ WETTS_DEVICE void tc_mma_tf32_split2(uint32_t d_tmem, uint32_t d_tmem_small, uin
       "r"(d_tmem_small), "l"(a_hi), "l"(a_lo), "l"(b_hilo), "r"(idesc_2n), "r"(idesc_n), "r"(accumulate_first)
       : "memory");
 }
+// one MMA of either kind, issued by one elected lane (used by tools/ubench and the f16-split kernels)
+WETTS_DEVICE void tc_mma_tf32_1(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, pa;\n\t}" ::"r"(d_tmem),
+      "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+WETTS_DEVICE void tc_mma_f16_1(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pa;\n\t}" ::"r"(d_tmem),
+      "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // A value every lane of the warp holds anyway, routed through a shuffle so that the compiler can PROVE it
 // warp-uniform: descriptor arithmetic then stays in uniform registers (UIADD3/UMOV feeding UTCHMMA directly).
 // Without this every tcgen05.mma operand takes an R2UR round trip (~90 cycles per MMA measured, see
@@ -204,6 +223,10 @@ WETTS_DEVICE uint64_t desc_with_lo(uint64_t base, uint32_t lo) {
 // kind::tf32 instruction descriptor: fp32 accumulate, tf32 A/B (both K-major), M = 128, N
 WETTS_DEVICE uint32_t idesc_tf32_m128(int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+}
+// kind::f16 instruction descriptor: fp32 accumulate, fp16 A/B (format 0, both K-major), M = 128, N; K = 16 per MMA
+WETTS_DEVICE uint32_t idesc_f16_m128(int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 }  // namespace tc
