@@ -21,8 +21,11 @@
  *     unless documented otherwise;
  *   - no hidden allocation after wetts_vits_finalize(): scratch comes from a
  *     caller-provided workspace sized by the matching *_workspace_bytes() query;
- *   - a finalized handle is immutable: concurrent calls on different streams
- *     with different workspaces are legal;
+ *   - a finalized handle holds no per-call state: concurrent calls on different
+ *     streams (and host threads) with different workspaces are legal; every
+ *     scratch value of a call, including the device scalar behind the one host
+ *     sync of the path, lives in that call's workspace.  Options must not be
+ *     changed while calls on the same handle are in flight;
  *   - output audio stays float in [-1, 1]; x32767 / int16 belongs to the caller
  *     (vits_model.cc:84-86, wetts/cli/model.py:60).
  * There is no CPU fallback anywhere behind this interface.
@@ -91,6 +94,13 @@ int wetts_vits_set_tensor(wetts_vits_t h, const char* name, const void* data, co
  * missing key.  Synchronous. */
 int wetts_vits_finalize(wetts_vits_t h);
 void wetts_vits_destroy(wetts_vits_t h);
+/* Per-handle options; they take precedence over the process-wide ones above.  "tensor_cores" and
+ * "fused_resblock" as above (value -1: follow the process-wide option again); "length_aware": 1 lets the
+ * generator skip tiles that lie wholly beyond an utterance's own length plus the receptive field when
+ * y_lengths is given (valid samples unchanged, the padded tail is left unspecified; default 0 = compute the
+ * full padded tail exactly as the reference does). */
+int wetts_vits_set_option(wetts_vits_t h, const char* name, int value);
+int wetts_vits_get_option(wetts_vits_t h, const char* name, int* value);
 /* product of upsample_rates (256 for every reference config; vits_model.h:27) */
 int wetts_vits_upsample_factor(wetts_vits_t h);
 
@@ -145,6 +155,11 @@ int wetts_flow_reverse(wetts_vits_t h, float* z, const int64_t* y_lengths, const
 size_t wetts_generator_workspace_bytes(wetts_vits_t h, int B, int T);
 int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_lengths, const float* g, int B, int T,
                             float* audio, void* workspace, size_t workspace_bytes, void* stream);
+/* Same on a strided view of z: element (b, c, t) at z[b*z_batch_stride + c*z_channel_stride + t], t < T.  This is
+ * how infer(max_len=...) vocodes (z * y_mask)[:, :, :max_len] without a copy (models.py:270-271). */
+int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch_stride, int64_t z_channel_stride,
+                                 const int64_t* y_lengths, const float* g, int B, int T, float* audio,
+                                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- whole path, split at the one unavoidable host sync (Ty = max y_lengths) */
 
@@ -161,12 +176,13 @@ int wetts_vits_infer_durations(wetts_vits_t h, const int64_t* ids, const int64_t
                                int64_t* y_lengths, float* logw_out, float* w_ceil_out, int* max_frames_host,
                                void* workspace, size_t workspace_bytes, void* stream);
 /* Stage 2: expand prior, sample, invert the flow, vocode.  Ty must be >= the
- * value stage 1 returned (normally equal).  Outputs (any may be NULL except
- * audio): audio f32[B,1,Ty*U], attn f32[B,1,Ty,Tx], y_mask f32[B,1,Ty],
- * z, z_p, m_p, logs_p f32[B,192,Ty]. */
+ * value stage 1 returned (normally equal).  gen_frames: number of leading frames
+ * the vocoder runs on -- infer()'s `max_len` (models.py:270-271); <= 0 or > Ty means Ty.
+ * Outputs (any may be NULL except audio): audio f32[B,1,gen_frames*U],
+ * attn f32[B,1,Ty,Tx], y_mask f32[B,1,Ty], z, z_p, m_p, logs_p f32[B,192,Ty]. */
 int wetts_vits_infer_synthesize(wetts_vits_t h, const int64_t* x_lengths, const int64_t* y_lengths,
                                 const float* scales3, const float* noise_z, int64_t noise_bs, int64_t noise_rs,
-                                int B, int Tx, int Ty, float* audio, float* attn, float* y_mask, float* z,
+                                int B, int Tx, int Ty, int gen_frames, float* audio, float* attn, float* y_mask, float* z,
                                 float* z_p, float* m_p, float* logs_p, void* workspace, size_t workspace_bytes,
                                 void* stream);
 

@@ -1,9 +1,11 @@
-"""Import and drive the REAL reference (`/root/reference/wetts/vits`) -- authoring container only.
+"""Import and drive the REAL reference (`wetts/vits` of wenet-e2e/wetts, unmodified).
 
-Test infrastructure (see oracle/vits_oracle.py header).  `/root/reference` does not exist
-on the GPU box, so nothing under tests/ (gpu-marked), smoke() or bench.py imports this
-module; it is used by oracle/gen_golden.py (fixture generation) and by the not-gpu test
-that cross-checks the oracle against the live reference when the tree is present.
+Test infrastructure (see oracle/vits_oracle.py header).  The tree is taken from `/root/reference`
+where it exists (authoring container) and otherwise from `oracle/_ref/wetts_vits/`, the byte-identical
+copy oracle/build_ref.py places there (git-ignored, travels to the GPU box).  Used by oracle/gen_golden.py
+(fixture generation), by the not-gpu test that cross-checks the oracle against the live reference, and by
+bench.py's CPU arm (`--impl reference`, `cpu_baseline`), where it is the thing TIMED as the baseline --
+never part of the product path.
 Recipe: SURVEY.md App. C (librosa stub before import; namespace-package imports).
 """
 import contextlib
@@ -15,11 +17,19 @@ import types
 import torch
 
 REFERENCE_ROOT = "/root/reference"
-_VITS_DIR = os.path.join(REFERENCE_ROOT, "wetts", "vits")
+# the reference tree where it lies (authoring container) or the byte-identical copy placed by oracle/build_ref.py
+# under oracle/_ref/ (git-ignored; travels to the GPU box)
+_CANDIDATES = (os.path.join(REFERENCE_ROOT, "wetts", "vits"),
+               os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "wetts_vits"))
+_VITS_DIR = next((d for d in _CANDIDATES if os.path.isfile(os.path.join(d, "model", "models.py"))), _CANDIDATES[0])
 
 
 def available():
-    return os.path.isdir(_VITS_DIR)
+    return os.path.isfile(os.path.join(_VITS_DIR, "model", "models.py"))
+
+
+def location():
+    return _VITS_DIR
 
 
 def _install_librosa_stub():

@@ -33,6 +33,8 @@ PROTOTYPES = {
     "wetts_version": (C.c_char_p, []),
     "wetts_set_option": (_I, [C.c_char_p, _I]),
     "wetts_get_option": (_I, [C.c_char_p, C.POINTER(_I)]),
+    "wetts_vits_set_option": (_I, [_P, C.c_char_p, _I]),
+    "wetts_vits_get_option": (_I, [_P, C.c_char_p, C.POINTER(_I)]),
     "wetts_vits_create": (_I, [C.POINTER(VitsConfig), _I, C.POINTER(_P)]),
     "wetts_vits_set_tensor": (_I, [_P, C.c_char_p, _P, C.POINTER(_I64), _I]),
     "wetts_vits_finalize": (_I, [_P]),
@@ -49,9 +51,10 @@ PROTOTYPES = {
     "wetts_flow_reverse": (_I, [_P, _P, _P, _P, _I, _I, _P, _SZ, _P]),
     "wetts_generator_workspace_bytes": (_SZ, [_P, _I, _I]),
     "wetts_generator_forward": (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _SZ, _P]),
+    "wetts_generator_forward_view": (_I, [_P, _P, _I64, _I64, _P, _P, _I, _I, _P, _P, _SZ, _P]),
     "wetts_vits_infer_workspace_bytes": (_SZ, [_P, _I, _I, _I]),
     "wetts_vits_infer_durations": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P, C.POINTER(_I), _P, _SZ, _P]),
-    "wetts_vits_infer_synthesize": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P,
+    "wetts_vits_infer_synthesize": (_I, [_P, _P, _P, _P, _P, _I64, _I64, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P,
                                          _SZ, _P]),
     "wetts_vits_decoder_workspace_bytes": (_SZ, [_P, _I, _I]),
     "wetts_vits_forward_decoder": (_I, [_P, _P, _P, _I, _I, _P, _P, _SZ, _P]),

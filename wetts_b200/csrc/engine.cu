@@ -20,6 +20,13 @@ namespace wetts {
 
 static thread_local std::string g_err;
 
+// Effective options of the call in progress on this host thread: the handle's own setting when it has one
+// (wetts_vits_set_option), else the process-wide default (wetts_set_option).  Set by CHECK_READY.
+struct CallOpts {
+  bool tc = true, fused = true, len_aware = false;
+};
+static thread_local CallOpts g_call;
+
 static int fail(const char* fmt, ...) {
   char buf[1024];
   va_list ap;
@@ -100,8 +107,8 @@ struct wetts_vits_s {
   bool finalized = false;
   std::map<std::string, Raw> raw;
   std::vector<void*> owned;
-  long long* host_pinned = nullptr;  // D2H landing zone for max(y_lengths)
-  long long* dev_scalar = nullptr;
+  // per-handle options: -1 = follow the process-wide option (wetts_set_option)
+  int opt_tc = -1, opt_fused = -1, opt_len_aware = 0;
   unsigned long long launches_at_create = 0;
   int U = 1;
 
@@ -282,6 +289,7 @@ static ConvArgs conv_args(const Conv& c, const float* in, long long in_bs, int i
   a.dil = dil;
   a.pad_left = (c.K - 1) * dil / 2;
   a.ep.out_bs = (long long)c.Cout * T;
+  a.use_tc = g_call.tc ? 1 : 0;
   return a;
 }
 
@@ -373,10 +381,6 @@ int wetts_vits_create(const wetts_vits_config* cfg, int device, wetts_vits_t* ou
   h->device = device;
   h->U = U;
   h->launches_at_create = kernel_launch_counter();
-  if (cudaMallocHost((void**)&h->host_pinned, 64) != cudaSuccess || cudaMalloc((void**)&h->dev_scalar, 64) != cudaSuccess) {
-    delete h;
-    return fail("allocation failed");
-  }
   *out = h;
   return 0;
 }
@@ -387,8 +391,6 @@ void wetts_vits_destroy(wetts_vits_t h) {
   cudaDeviceSynchronize();
   for (void* p : h->owned) cudaFree(p);
   for (auto& kv : h->raw) cudaFree(kv.second.d);
-  if (h->host_pinned) cudaFreeHost(h->host_pinned);
-  if (h->dev_scalar) cudaFree(h->dev_scalar);
   delete h;
 }
 
@@ -417,6 +419,22 @@ int wetts_get_option(const char* name, int* value) {
     return 0;
   }
   return fail("unknown option '%s'", name);
+}
+int wetts_vits_set_option(wetts_vits_t h, const char* name, int value) {
+  if (!h || !name) return fail("null argument");
+  if (!strcmp(name, "tensor_cores")) h->opt_tc = value < 0 ? -1 : (value != 0);
+  else if (!strcmp(name, "fused_resblock")) h->opt_fused = value < 0 ? -1 : (value != 0);
+  else if (!strcmp(name, "length_aware")) h->opt_len_aware = value != 0;
+  else return fail("unknown option '%s'", name);
+  return 0;
+}
+int wetts_vits_get_option(wetts_vits_t h, const char* name, int* value) {
+  if (!h || !name || !value) return fail("null argument");
+  if (!strcmp(name, "tensor_cores")) *value = h->opt_tc >= 0 ? h->opt_tc : (tensor_cores_enabled() ? 1 : 0);
+  else if (!strcmp(name, "fused_resblock")) *value = h->opt_fused >= 0 ? h->opt_fused : (fused_resblock_enabled() ? 1 : 0);
+  else if (!strcmp(name, "length_aware")) *value = h->opt_len_aware;
+  else return fail("unknown option '%s'", name);
+  return 0;
 }
 int wetts_audio_to_int16(const float* audio, const int64_t* lengths, int B, int64_t L, int mode, float* peak_scratch,
                          int16_t* out, void* stream) {
@@ -660,10 +678,13 @@ int wetts_vits_finalize(wetts_vits_t h) {
   return 0;
 }
 
-#define CHECK_READY(h)                                     \
-  if (!(h)) return fail("null handle");                    \
-  if (!(h)->finalized) return fail("handle not finalized"); \
-  CUDA_OK(cudaSetDevice((h)->device));
+#define CHECK_READY(h)                                                                        \
+  if (!(h)) return fail("null handle");                                                       \
+  if (!(h)->finalized) return fail("handle not finalized");                                   \
+  CUDA_OK(cudaSetDevice((h)->device));                                                        \
+  g_call.tc = ((h)->opt_tc >= 0 ? (h)->opt_tc != 0 : tensor_cores_enabled());                 \
+  g_call.fused = ((h)->opt_fused >= 0 ? (h)->opt_fused != 0 : fused_resblock_enabled());      \
+  g_call.len_aware = (h)->opt_len_aware != 0;
 
 #define CHECK_LAUNCH()                                                                                   \
   do {                                                                                                   \
@@ -976,8 +997,16 @@ size_t wetts_generator_workspace_bytes(wetts_vits_t h, int B, int T) {
 }
 int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_lengths, const float* g, int B, int T,
                             float* audio, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return fail("null handle");
+  return wetts_generator_forward_view(h, z, (int64_t)h->cfg.inter_channels * T, T, y_lengths, g, B, T, audio, workspace,
+                                      workspace_bytes, stream);
+}
+int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch_stride, int64_t z_channel_stride,
+                                 const int64_t* y_lengths, const float* g, int B, int T, float* audio, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
   CHECK_READY(h);
   if (B <= 0 || T <= 0) return fail("empty batch");
+  if (z_channel_stride < T || z_channel_stride > 0x7fffffff) return fail("bad channel stride");
   const wetts_vits_config& c = h->cfg;
   cudaStream_t s = (cudaStream_t)stream;
   Arena A(workspace, workspace_bytes);
@@ -986,7 +1015,8 @@ int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_len
   if (!workspace || !A.ok()) return fail("generator workspace too small: need %zu bytes", A.off);
   const int Cc = c.inter_channels;
   const bool has_g = g && c.gin_channels > 0;
-  ConvArgs a = conv_args(h->conv_pre, z, (long long)Cc * T, T, B, T);
+  (void)Cc;
+  ConvArgs a = conv_args(h->conv_pre, z, (long long)z_batch_stride, (int)z_channel_stride, B, T);
   if (y_lengths) { a.lengths = (const long long*)y_lengths; a.in_mask = 1; }
   if (has_g) {
     cond_vector(h->dec_cond, g, B, w.cvec, s);
@@ -1003,7 +1033,8 @@ int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_len
     ConvTArgs ta;
     ta.in = w.x[cur]; ta.w = up.w; ta.bias = up.b; ta.out = w.xu; ta.B = B; ta.Cin = up.Cin; ta.Cout = up.Cout;
     ta.CoutPad = up.CoutPad; ta.T = len; ta.u = up.u; ta.ntaps = up.ntaps; ta.pad = up.pad; ta.pre_slope = 0.1f;
-    if (up.as_conv.wtc && tensor_cores_enabled() && len + 1 >= 64) {
+    // polyphase form needs the tcgen05 kernel (EPI_CONVT / in_T exist only there) and exactly two taps per phase
+    if (up.as_conv.wtc && g_call.tc && up.ntaps == 2 && len + up.ntaps - 1 >= 64 && up.as_conv.tc.dil == 1) {
       // polyphase form on the tensor pipe: a 2-tap conv over the input frames with Cout*u packed channels
       ConvArgs ca = conv_args(up.as_conv, w.x[cur], (long long)up.Cin * len, len, B, len, 1);
       ca.T = len + up.ntaps - 1;       // frames q = 0 .. len + ntaps - 2 reach output samples
@@ -1012,7 +1043,7 @@ int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_len
       ca.pre_act = 1; ca.pre_slope = 0.1f;
       ca.ep.mode = EPI_CONVT; ca.ep.out = w.xu; ca.ep.out_bs = (long long)up.Cout * len * up.u;
       ca.ep.up_u = up.u; ca.ep.up_pad = up.pad; ca.ep.out_T = (long long)len * up.u;
-      launch_conv1d(ca, s);
+      launch_conv1d_tc(ca, s);
     } else {
       launch_conv_transpose1d(ta, s);
     }
@@ -1020,7 +1051,7 @@ int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_len
     const int ch = up.Cout;
     const long long bs = (long long)ch * len;
     float* acc = w.x[cur ^ 1];
-    if (h->fused_rb_w[i] && tensor_cores_enabled() && fused_resblock_enabled() && (len & 3) == 0) {   // 16 B row loads
+    if (h->fused_rb_w[i] && g_call.tc && g_call.fused && (len & 3) == 0) {   // 16 B row loads
       FusedRbArgs fa;
       fa.in = w.xu; fa.out = acc; fa.w = h->fused_rb_w[i];
       fa.B = B; fa.T = len; fa.nrb = nk; fa.slope = 0.1f; fa.div = (float)nk;
@@ -1075,6 +1106,7 @@ int wetts_generator_forward(wetts_vits_t h, const float* z, const int64_t* y_len
 // ------------------------------------------------------------------ whole path
 struct InferWs {
   float *g, *hbuf, *m, *logs, *logw, *w_ceil, *zbuf;
+  long long* scalar;   // per-call device scalar (max y_lengths): lives in the caller's workspace, not in the handle
   int* cum;
   void* scratch;
   size_t scratch_bytes;
@@ -1089,6 +1121,7 @@ static size_t infer_layout(wetts_vits_t h, int B, int Tx, int max_frames, Arena&
   w->logw = A.take<float>(n);
   w->w_ceil = A.take<float>(n);
   w->cum = A.take<int>(n);
+  w->scalar = A.take<long long>(8);
   w->zbuf = A.take<float>((size_t)B * c.inter_channels * max_frames);
   size_t s1 = wetts_text_encoder_workspace_bytes(h, B, Tx);
   size_t s2 = wetts_duration_workspace_bytes(h, B, Tx);
@@ -1134,21 +1167,25 @@ int wetts_vits_infer_durations(wetts_vits_t h, const int64_t* ids, const int64_t
   if (wetts_text_encoder_forward(h, ids, x_lengths, B, Tx, w.hbuf, w.m, w.logs, tail, tail_bytes, stream)) return 1;
   if (wetts_duration_forward(h, w.hbuf, x_lengths, g, noise_w, scales3[2], B, Tx, w.logw, tail, tail_bytes, stream)) return 1;
   if (wetts_length_regulate(h, w.logw, x_lengths, durations, scales3[1], B, Tx, w.w_ceil, w.cum, y_lengths, stream)) return 1;
-  launch_max_i64((const long long*)y_lengths, B, h->dev_scalar, s);
-  CUDA_OK(cudaMemcpyAsync(h->host_pinned, h->dev_scalar, sizeof(long long), cudaMemcpyDeviceToHost, s));
+  launch_max_i64((const long long*)y_lengths, B, w.scalar, s);
   if (logw_out) CUDA_OK(cudaMemcpyAsync(logw_out, w.logw, sizeof(float) * B * Tx, cudaMemcpyDeviceToDevice, s));
   if (w_ceil_out) CUDA_OK(cudaMemcpyAsync(w_ceil_out, w.w_ceil, sizeof(float) * B * Tx, cudaMemcpyDeviceToDevice, s));
+  // the one host sync of the path (Ty sizes the outputs): the landing zone is this call's stack, no handle state
+  long long max_frames = 0;
+  CUDA_OK(cudaMemcpyAsync(&max_frames, w.scalar, sizeof(long long), cudaMemcpyDeviceToHost, s));
   CUDA_OK(cudaStreamSynchronize(s));
-  *max_frames_host = (int)h->host_pinned[0];
+  CHECK_LAUNCH();
+  *max_frames_host = (int)max_frames;
   return 0;
 }
 
 int wetts_vits_infer_synthesize(wetts_vits_t h, const int64_t* x_lengths, const int64_t* y_lengths, const float* scales3,
                                 const float* noise_z, int64_t noise_bs, int64_t noise_rs, int B, int Tx, int Ty,
-                                float* audio, float* attn, float* y_mask, float* z, float* z_p, float* m_p, float* logs_p,
-                                void* workspace, size_t workspace_bytes, void* stream) {
+                                int gen_frames, float* audio, float* attn, float* y_mask, float* z, float* z_p, float* m_p,
+                                float* logs_p, void* workspace, size_t workspace_bytes, void* stream) {
   CHECK_READY(h);
   if (!audio || !scales3 || !noise_z) return fail("null argument");
+  if (gen_frames <= 0 || gen_frames > Ty) gen_frames = Ty;
   cudaStream_t s = (cudaStream_t)stream;
   Arena A(workspace, workspace_bytes);
   InferWs w;
@@ -1164,7 +1201,10 @@ int wetts_vits_infer_synthesize(wetts_vits_t h, const int64_t* x_lengths, const 
   if (zp_dst != zb)
     CUDA_OK(cudaMemcpyAsync(zb, zp_dst, sizeof(float) * (size_t)B * c.inter_channels * Ty, cudaMemcpyDeviceToDevice, s));
   if (wetts_flow_reverse(h, zb, y_lengths, g, B, Ty, w.scratch, w.scratch_bytes, stream)) return 1;
-  if (wetts_generator_forward(h, zb, y_lengths, g, B, Ty, audio, w.scratch, w.scratch_bytes, stream)) return 1;
+  // models.py:270-271: the vocoder sees (z * y_mask)[:, :, :max_len] -- the flow ran on all Ty frames
+  if (wetts_generator_forward_view(h, zb, (int64_t)c.inter_channels * Ty, Ty, y_lengths, g, B, gen_frames, audio, w.scratch,
+                                   w.scratch_bytes, stream))
+    return 1;
   return 0;
 }
 

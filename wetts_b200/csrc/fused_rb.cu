@@ -58,7 +58,7 @@ int dyn_smem_offset(uint32_t* off, cudaStream_t s) {
   return 0;
 }
 
-static bool g_fused_rb = true;
+static std::atomic<bool> g_fused_rb{true};
 void set_fused_resblock_enabled(bool on) { g_fused_rb = on; }
 bool fused_resblock_enabled() { return g_fused_rb; }
 

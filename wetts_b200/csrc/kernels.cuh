@@ -62,6 +62,7 @@ struct ConvArgs {
   float pre_slope = 0.1f;
   const long long* lengths = nullptr;  // int64[B] or nullptr
   int in_mask = 0;            // multiply the input by (t < lengths[b])
+  int use_tc = 1;             // 0: force the fp32 SIMT kernel for this call (per-handle / process option)
   ConvEpilogue ep;
 };
 void launch_conv1d(const ConvArgs& a, cudaStream_t s);

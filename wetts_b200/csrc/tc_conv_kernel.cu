@@ -18,6 +18,7 @@
 // * Weights arrive by cp.async.bulk (TMA 1-D bulk copy) + mbarrier; tcgen05.commit signals
 //   buffer reuse and accumulator completion; one persistent CTA per SM loops over work items
 //   and keeps the weight tile resident when it can.
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -569,7 +570,7 @@ void launch_pack_conv_tc(const float* src, float* dst, const int* co_map, const 
   count_launch();
 }
 
-static bool g_tc_enabled = true;
+static std::atomic<bool> g_tc_enabled{true};
 void set_tensor_cores_enabled(bool on) { g_tc_enabled = on; }
 bool tensor_cores_enabled() { return g_tc_enabled; }
 

@@ -42,7 +42,8 @@ def _lengths_from_mask(mask):
 
 
 class _Engine:
-    """Owns the C handle, the uploaded checkpoint and a grow-only device workspace."""
+    """Owns the C handle, the uploaded checkpoint and one grow-only device workspace PER STREAM
+    (calls on different streams may overlap; each must have its own scratch, include/wetts_b200.h)."""
 
     def __init__(self, cfg: VitsConfig):
         self.cfg = cfg
@@ -51,7 +52,7 @@ class _Engine:
         self.device = None
         self.pending = {}
         self.finalized = False
-        self._ws = None
+        self._ws = {}
 
     # -- lifetime -----------------------------------------------------------
     def attach(self, device):
@@ -77,7 +78,7 @@ class _Engine:
             self.lib.wetts_vits_destroy(self.handle)
             self.handle = None
             self.finalized = False
-            self._ws = None
+            self._ws = {}
 
     def __del__(self):
         try:
@@ -106,11 +107,18 @@ class _Engine:
         if not self.finalized:
             raise WettsError("no checkpoint loaded: call load_state_dict() / load_checkpoint() first")
 
-    def workspace(self, nbytes):
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self._ws
+    def workspace(self, nbytes, keep_prefix=0):
+        """Scratch of the current stream, grown when needed; `keep_prefix` bytes of the old buffer are carried
+        over (stage-1 results of infer() live in the prefix of the stage-2 workspace)."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            new = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+            if ws is not None and keep_prefix:
+                n = min(ws.numel(), int(keep_prefix))
+                new[:n].copy_(ws[:n])
+            self._ws[key] = ws = new
+        return ws
 
     @property
     def upsample(self):
@@ -301,6 +309,13 @@ class SynthesizerTrn:
     def launch_count(self):
         return self._engine.launch_count()
 
+    def set_option(self, name, value):
+        """Per-model engine option ("tensor_cores", "fused_resblock", "length_aware"); see include/wetts_b200.h."""
+        e = self._engine
+        e.ready()
+        check(e.lib.wetts_vits_set_option(e.handle, name.encode(), int(value)))
+        return self
+
     # -- inference ------------------------------------------------------------
     @torch.no_grad()
     def infer(self, x, x_lengths, sid=None, noise_scale=1, length_scale=1, noise_scale_w=1.0, max_len=None, *,
@@ -336,12 +351,7 @@ class SynthesizerTrn:
         # stage 2
         nbytes2 = e.lib.wetts_vits_infer_workspace_bytes(e.handle, B, Tx, Ty)
         if nbytes2 > ws.numel():
-            # grow, preserving the stage-1 results that live in the prefix of the workspace
-            old = ws
-            e._ws = None
-            ws = e.workspace(nbytes2)
-            ws[: min(old.numel(), nbytes1)].copy_(old[: min(old.numel(), nbytes1)])
-            del old
+            ws = e.workspace(nbytes2, keep_prefix=nbytes1)   # grow, preserving the stage-1 results in the prefix
         Cc = self.inter_channels
         if noise_z is None:
             noise_z = torch.randn(B, Cc, Ty, device=dev)
@@ -350,17 +360,17 @@ class SynthesizerTrn:
             if noise_z.shape[2] < Ty:
                 raise ValueError(f"noise_z has {noise_z.shape[2]} frames, need {Ty}")
         U = e.upsample
-        o = torch.empty(B, 1, Ty * U, device=dev, dtype=torch.float32)
+        # models.py:270-271: the vocoder runs on (z * y_mask)[:, :, :max_len]; everything before it on all Ty frames
+        Tg = Ty if max_len is None else max(1, min(Ty, int(max_len)))
+        o = torch.empty(B, 1, Tg * U, device=dev, dtype=torch.float32)
         attn = torch.empty(B, 1, Ty, Tx, device=dev, dtype=torch.float32) if return_attn else None
         y_mask = torch.empty(B, 1, Ty, device=dev, dtype=torch.float32)
         z = torch.empty(B, Cc, Ty, device=dev, dtype=torch.float32)
         z_p, m_p, logs_p = torch.empty_like(z), torch.empty_like(z), torch.empty_like(z)
         check(e.lib.wetts_vits_infer_synthesize(e.handle, _ptr(x_lengths), _ptr(y_lengths), scales, _ptr(noise_z),
-                                                noise_z.stride(0), noise_z.stride(1), B, Tx, Ty, _ptr(o), _ptr(attn),
+                                                noise_z.stride(0), noise_z.stride(1), B, Tx, Ty, Tg, _ptr(o), _ptr(attn),
                                                 _ptr(y_mask), _ptr(z), _ptr(z_p), _ptr(m_p), _ptr(logs_p), _ptr(ws),
                                                 ws.numel(), st))
-        if max_len is not None:
-            o = o[:, :, : max_len * U]
         self.last_y_lengths = y_lengths
         return o, attn, y_mask, (z, z_p, m_p, logs_p)
 
