@@ -324,6 +324,8 @@ def run_ours(args):
     lib = _lib.load()
     _lib.check(lib.wetts_set_option(b"tensor_cores", int(args.tensor_cores)))
     _lib.check(lib.wetts_set_option(b"fused_resblock", int(args.fused_resblock)))
+    if args.tensor_format:
+        _lib.check(lib.wetts_set_option(b"tensor_format", int(args.tensor_format)))
     hps = builtin_config(cfg_name)
     sd = synth.make_state_dict(hps.model, wl["n_vocab"], wl["n_spk"], seed=hps.train.seed)
     net = wetts_b200.build_model(hps, wl["n_vocab"], wl["n_spk"], sd, dev)
@@ -622,6 +624,8 @@ def main():
                     help="wrap the timed region in cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     ap.add_argument("--tensor-cores", type=int, default=1, help="0: force the fp32 SIMT kernels")
     ap.add_argument("--fused-resblock", type=int, default=1, help="0: one launch per generator conv (no fused MRF stage kernel)")
+    ap.add_argument("--tensor-format", type=int, default=0, choices=[0, 16, 32],
+                    help="operand format of the fused stage kernels: 16 = f16 split, 32 = 3xTF32, 0 = library default")
     ap.add_argument("--length-aware", type=int, default=0, help="1: skip generator tiles beyond each utterance's own length")
     args = ap.parse_args()
     if args.impl == "reference":

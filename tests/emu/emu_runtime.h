@@ -37,6 +37,9 @@
 struct alignas(16) float4 {
   float x, y, z, w;
 };
+struct alignas(16) uint4 {
+  uint32_t x, y, z, w;
+};
 #endif
 
 namespace emu {
@@ -53,6 +56,7 @@ struct MBar {
 };
 struct Op {
   enum Kind { MMA, COMMIT } kind;
+  int mma_kind = 32;   // 32: kind::tf32 (K = 8, 4-byte elements), 16: kind::f16 (K = 16, 2-byte elements)
   uint32_t d_tmem = 0, idesc = 0, accumulate = 0, bar = 0;
   uint64_t adesc = 0, bdesc = 0;
 };
@@ -118,7 +122,13 @@ inline void exec_mma(const Op& o) {
   Cta* c = cta();
   const uint32_t N = ((o.idesc >> 17) & 0x3F) << 3, M = ((o.idesc >> 24) & 0x1F) << 4;
   if (M != 128) die("only M = 128 is modelled");
-  if (((o.idesc >> 4) & 3) != 1 || ((o.idesc >> 7) & 7) != 2 || ((o.idesc >> 10) & 7) != 2) die("idesc: expected f32 += tf32*tf32");
+  if (N < 16 || N > 256 || (N & 15)) die("idesc: N must be a multiple of 16 in [16, 256] for M = 128");
+  const uint32_t afmt = (o.idesc >> 7) & 7, bfmt = (o.idesc >> 10) & 7;
+  if (((o.idesc >> 4) & 3) != 1) die("idesc: expected an f32 accumulator");
+  const bool f16 = (o.mma_kind == 16);
+  if (f16 ? (afmt != 0 || bfmt != 0) : (afmt != 2 || bfmt != 2)) die("idesc: operand formats do not match the MMA kind");
+  if ((o.idesc >> 15) & 3) die("idesc: only K-major operands are modelled");
+  const uint32_t K = f16 ? 16 : 8, kpc = f16 ? 8 : 4, esz = f16 ? 2 : 4;
   auto field = [](uint64_t d, int sh) { return (uint32_t)((d >> sh) & 0x3FFF) << 4; };
   const uint32_t a0 = field(o.adesc, 0), a_lbo = field(o.adesc, 16), a_sbo = field(o.adesc, 32);
   const uint32_t b0 = field(o.bdesc, 0), b_lbo = field(o.bdesc, 16), b_sbo = field(o.bdesc, 32);
@@ -128,21 +138,26 @@ inline void exec_mma(const Op& o) {
   if ((o.d_tmem >> 16) != 0) die("MMA accumulator must start at TMEM lane 0");
   if (col0 + N > c->tmem_alloc_cols) die("MMA accumulator outside the TMEM allocation");
   auto elem = [&](uint32_t start, uint32_t lbo, uint32_t sbo, uint32_t row, uint32_t k) {
-    const uint32_t addr = start + (k / 4) * lbo + (row / 8) * sbo + (row % 8) * 16 + (k % 4) * 4;
+    const uint32_t addr = start + (k / kpc) * lbo + (row / 8) * sbo + (row % 8) * 16 + (k % kpc) * esz;
+    if (f16) {
+      _Float16 h;
+      memcpy(&h, smem_ptr(addr, 2), 2);
+      return (float)h;
+    }
     float v;
     memcpy(&v, smem_ptr(addr, 4), 4);
     return tf32_trunc(v);
   };
-  std::vector<float> bm((size_t)N * 8);
+  std::vector<float> bm((size_t)N * K);
   for (uint32_t n = 0; n < N; ++n)
-    for (uint32_t k = 0; k < 8; ++k) bm[n * 8 + k] = elem(b0, b_lbo, b_sbo, n, k);
+    for (uint32_t k = 0; k < K; ++k) bm[n * K + k] = elem(b0, b_lbo, b_sbo, n, k);
   for (uint32_t m = 0; m < 128; ++m) {
-    float a[8];
-    for (uint32_t k = 0; k < 8; ++k) a[k] = elem(a0, a_lbo, a_sbo, m, k);
+    float a[16];
+    for (uint32_t k = 0; k < K; ++k) a[k] = elem(a0, a_lbo, a_sbo, m, k);
     for (uint32_t n = 0; n < N; ++n) {
-      // products of tf32 values are exact; the tensor core accumulates wide, modelled with double
+      // products of tf32 / f16 values are exact; the tensor core accumulates wide, modelled with double
       double s = 0.0;
-      for (uint32_t k = 0; k < 8; ++k) s += (double)a[k] * (double)bm[n * 8 + k];
+      for (uint32_t k = 0; k < K; ++k) s += (double)a[k] * (double)bm[n * K + k];
       float& d = c->tmem[m][col0 + n];
       d = o.accumulate ? (float)((double)d + s) : (float)s;
     }
@@ -195,6 +210,7 @@ WETTS_DEVICE void warp_sync() { emu::cta()->warp_bars[emu::g_tid >> 5]->arrive_a
 WETTS_DEVICE float ldg(const float* p) { return *p; }
 WETTS_DEVICE long long clock_now() { return 0; }
 WETTS_DEVICE void trap_now() { emu::die("kernel trap"); }
+WETTS_DEVICE int ldg_i32(const int* p) { return *p; }
 WETTS_DEVICE float4 ldg4(const float* p) {
   if ((uintptr_t)p & 15) emu::die("16 B load from a misaligned address");
   return *reinterpret_cast<const float4*>(p);
@@ -288,6 +304,46 @@ WETTS_DEVICE void tc_mma_tf32_split2(uint32_t d_tmem, uint32_t d_tmem_small, uin
   emu::cta()->queue.push_back(o);
   o.d_tmem = d_tmem_small; o.idesc = idesc_n; o.adesc = a_lo; o.bdesc = b_hilo; o.accumulate = 1;
   emu::cta()->queue.push_back(o);
+}
+WETTS_DEVICE void emu_push_mma(int kind, uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  if ((emu::g_tid & 31) != 0) return;
+  std::lock_guard<std::mutex> g(emu::cta()->m);
+  emu::Op o;
+  o.kind = emu::Op::MMA;
+  o.mma_kind = kind;
+  o.d_tmem = d_tmem; o.idesc = idesc; o.adesc = a; o.bdesc = b; o.accumulate = accumulate;
+  emu::cta()->queue.push_back(o);
+}
+WETTS_DEVICE void tc_mma_tf32_1(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  emu_push_mma(32, d_tmem, a, b, idesc, accumulate);
+}
+WETTS_DEVICE void tc_mma_f16_1(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+  emu_push_mma(16, d_tmem, a, b, idesc, accumulate);
+}
+WETTS_DEVICE void tc_mma_f16_split2(uint32_t d_tmem, uint32_t d_tmem_small, uint64_t a_hi, uint64_t a_lo, uint64_t b_hilo,
+                                    uint32_t idesc_2n, uint32_t idesc_n, uint32_t accumulate_first) {
+  emu_push_mma(16, d_tmem, a_hi, b_hilo, idesc_2n, accumulate_first);
+  emu_push_mma(16, d_tmem_small, a_lo, b_hilo, idesc_n, 1u);
+}
+// f16 split pair (see tc_prims.cuh): element 0 in the low half
+WETTS_DEVICE uint32_t f16x2_pack(float lo_elem, float hi_elem) {
+  auto cv = [](float x) {
+    if (x > 65504.f) x = 65504.f;          // satfinite
+    if (x < -65504.f) x = -65504.f;
+    _Float16 h = (_Float16)x;
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return (uint32_t)u;
+  };
+  return cv(lo_elem) | (cv(hi_elem) << 16);
+}
+WETTS_DEVICE void f16x2_unpack(uint32_t v, float& lo_elem, float& hi_elem) {
+  uint16_t a = (uint16_t)(v & 0xFFFF), b = (uint16_t)(v >> 16);
+  _Float16 ha, hb;
+  memcpy(&ha, &a, 2);
+  memcpy(&hb, &b, 2);
+  lo_elem = (float)ha;
+  hi_elem = (float)hb;
 }
 WETTS_DEVICE uint32_t warp_uniform(uint32_t v) { return v; }
 WETTS_DEVICE uint32_t uniform_bits(uint32_t v, int lo, int hi) { return v & (((hi >= 32) ? 0xFFFFFFFFu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u)); }

@@ -1,0 +1,166 @@
+// CPU check of fused_mrf16_kernel (wetts_b200/csrc/fused_mrf16_kernel.cuh) in the CTA emulator: the kernel source is
+// compiled for the host and compared with a direct fp64 evaluation of ResBlock1 / ResBlock2 x nrb + MRF mean
+// (decoders.py:157-170, :205-214, :72-76).
+//   usage: fused_mrf16_emu type C B T grid [nrb] [ring slots: 4 | 6] [threads] [length-aware: 0 | 1]
+#define WETTS_EMULATE 1
+#include <math.h>
+
+#include <random>
+
+#include "fused_mrf16_kernel.cuh"
+
+using namespace wetts;
+
+static double lrelu_d(double x, double s) { return x > 0 ? x : x * s; }
+
+// y[co][t] = bias[co] + sum_{ci,tap} w[co][ci][tap] * lrelu(x)[ci][t + (tap - (k-1)/2)*d]   (zero padded)
+static void conv_ref(const std::vector<double>& x, std::vector<double>& y, const std::vector<float>& w,
+                     const std::vector<float>& bias, int C, int T, int k, int d, double slope) {
+  for (int co = 0; co < C; ++co)
+    for (int t = 0; t < T; ++t) {
+      double s = bias[co];
+      for (int ci = 0; ci < C; ++ci)
+        for (int tap = 0; tap < k; ++tap) {
+          const int ti = t + (tap - (k - 1) / 2) * d;
+          if (ti >= 0 && ti < T) s += (double)w[((size_t)co * C + ci) * k + tap] * lrelu_d(x[(size_t)ci * T + ti], slope);
+        }
+      y[(size_t)co * T + t] = s;
+    }
+}
+
+template <int C, int THREADS, int NB, int RP, bool TWO>
+static int run(int type, int B, int T, int grid, int nrb, int len_aware) {
+  // ResBlock2: v3 recipe kernels 3,5,7 with dilations (1,2),(2,6),(3,12); ResBlock1: v1 recipe 3,7,11 with (1,3,5)
+  const int ks2[3] = {3, 5, 7}, d2a[3] = {1, 2, 3}, d2b[3] = {2, 6, 12};
+  const int ks1[3] = {3, 7, 11};
+  std::mt19937 rng(4321 + C + T + type);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  std::vector<float> x((size_t)B * C * T), out((size_t)B * C * T, -777.f);
+  for (auto& v : x) v = nd(rng);
+  FusedMrfArgs a;
+  a.B = B; a.T = T; a.nrb = nrb; a.slope = 0.1f; a.div = (float)nrb; a.type = type; a.nconv = (type == 1) ? 6 : 2;
+  std::vector<std::vector<float>> w((size_t)nrb * a.nconv), bia((size_t)nrb * a.nconv);
+  int Hmax = 0;
+  size_t packed_halfs = 0;
+  for (int j = 0; j < nrb; ++j) {
+    a.k[j] = (type == 1) ? ks1[j] : ks2[j];
+    for (int c = 0; c < a.nconv; ++c) {
+      a.dil[j][c] = (type == 1) ? ((c & 1) ? 1 : 1 + 2 * (c / 2)) : (c ? d2b[j] : d2a[j]);
+      const float sc = 1.0f / sqrtf((float)(C * a.k[j]));
+      auto& ww = w[(size_t)j * a.nconv + c];
+      auto& bb = bia[(size_t)j * a.nconv + c];
+      ww.resize((size_t)C * C * a.k[j]);
+      bb.resize(C);
+      for (auto& v : ww) v = nd(rng) * sc;
+      for (auto& v : bb) v = nd(rng) * 0.1f;
+      a.bias[j][c] = bb.data();
+      packed_halfs += fused_mrf16_conv_halfs(C, a.k[j]);
+    }
+    const int H = fused_mrf16_halo(a, j);
+    Hmax = H > Hmax ? H : Hmax;
+  }
+  fused_mrf16_finalize_args(a, C);
+  if (RP < 128 + 2 * ((Hmax + 3) & ~3)) { printf("row pitch %d too small for halo %d\n", RP, Hmax); return 64; }
+  if ((size_t)a.nq * fused_mrf16_chunk_bytes(C) != packed_halfs * 2) { printf("chunk accounting mismatch\n"); return 1; }
+  if (NB == 6 && a.nq % 6 != 0) { printf("6-slot ring needs nq %% 6 == 0 (nq = %d)\n", a.nq); return 64; }
+  if (fused_mrf16_smem_bytes(C, NB, RP, TWO ? 2 : 1) > emu::kSmemBytes) { printf("smem over budget\n"); return 1; }
+  uint16_t* packed = (uint16_t*)aligned_alloc(128, packed_halfs * 2);
+  {
+    size_t off = 0;
+    for (int j = 0; j < nrb; ++j)
+      for (int c = 0; c < a.nconv; ++c) {
+        const auto& ww = w[(size_t)j * a.nconv + c];
+        const long long n = (long long)fused_mrf16_conv_halfs(C, a.k[j]);
+        for (long long i = 0; i < n; ++i) {
+          const FusedMrfPackIdx ix = fused_mrf16_pack_index(i, C);
+          const float v = ww[((size_t)ix.co * C + ix.ci) * a.k[j] + ix.tap];
+          uint32_t hi2, lo2;
+          tc::f16_split2(v, 0.f, hi2, lo2);
+          packed[off + i] = (uint16_t)((ix.hl ? lo2 : hi2) & 0xFFFF);
+        }
+        off += n;
+      }
+  }
+  a.in = x.data(); a.out = out.data(); a.w = packed;
+  a.smem_off = emu::kSmemBase;
+  // length-aware: utterance b computes only its first tiles (lengths 60 %, 100 %, 35 %, ... of T); the rest stays -777
+  std::vector<int> prefix(B + 1, 0), ntile(B);
+  const int n_tt = (T + 127) / 128;
+  for (int b = 0; b < B; ++b) {
+    const int pct[4] = {60, 100, 35, 80};
+    ntile[b] = len_aware ? std::max(1, (n_tt * pct[b & 3] + 99) / 100) : n_tt;
+    prefix[b + 1] = prefix[b] + ntile[b];
+  }
+  std::vector<int2_t> item_map;
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < ntile[b]; ++i) item_map.push_back(int2_t{b, i * 128});
+  const int n_items_host = (int)item_map.size();
+  if (len_aware) { a.item_map = item_map.data(); a.n_items_dev = &n_items_host; }
+  unsigned long long n_mma = 0;
+  emu::launch(fused_mrf16_kernel<C, THREADS, 1, NB, RP, TWO>, a, grid, THREADS, &n_mma);
+
+  // reference
+  double max_err = 0, sq = 0;
+  long long cnt = 0;
+  int untouched_ok = 1;
+  for (int b = 0; b < B; ++b) {
+    std::vector<double> xb((size_t)C * T), acc((size_t)C * T, 0.0), y((size_t)C * T), y2((size_t)C * T), cur((size_t)C * T);
+    for (size_t i = 0; i < xb.size(); ++i) xb[i] = x[(size_t)b * C * T + i];
+    for (int j = 0; j < nrb; ++j) {
+      cur = xb;
+      if (type == 2) {
+        for (int c = 0; c < 2; ++c) {
+          conv_ref(cur, y, w[(size_t)j * 2 + c], bia[(size_t)j * 2 + c], C, T, a.k[j], a.dil[j][c], 0.1);
+          for (size_t i = 0; i < y.size(); ++i) cur[i] = y[i] + cur[i];
+        }
+      } else {
+        for (int n = 0; n < 3; ++n) {
+          conv_ref(cur, y, w[(size_t)j * 6 + 2 * n], bia[(size_t)j * 6 + 2 * n], C, T, a.k[j], a.dil[j][2 * n], 0.1);
+          conv_ref(y, y2, w[(size_t)j * 6 + 2 * n + 1], bia[(size_t)j * 6 + 2 * n + 1], C, T, a.k[j], 1, 0.1);
+          for (size_t i = 0; i < y.size(); ++i) cur[i] = y2[i] + cur[i];
+        }
+      }
+      for (size_t i = 0; i < acc.size(); ++i) acc[i] += cur[i];
+    }
+    const int t_done = std::min(T, ntile[b] * 128);
+    for (int c = 0; c < C; ++c)
+      for (int t = 0; t < T; ++t) {
+        const size_t i = (size_t)c * T + t;
+        const double got = out[(size_t)b * C * T + i];
+        if (t >= t_done) { untouched_ok = untouched_ok && (got == -777.0); continue; }
+        const double ref = acc[i] / nrb;
+        const double e = fabs(ref - got);
+        max_err = e > max_err ? e : max_err;
+        sq += ref * ref;
+        ++cnt;
+      }
+  }
+  const double rms = sqrt(sq / (double)cnt);
+  printf("type=%d C=%d thr=%d ring=%d RP=%d B=%d T=%d grid=%d nrb=%d la=%d: mma=%llu max_err=%.3e rms=%.3e rel=%.3e untouched=%d\n", type, C,
+         THREADS, NB, RP, B, T, grid, nrb, len_aware, n_mma, max_err, rms, max_err / rms, untouched_ok);
+  free(packed);
+  return (max_err / rms < 2e-5 && untouched_ok) ? 0 : 2;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 6) { printf("usage: %s type C B T grid [nrb] [ring] [threads] [length-aware]\n", argv[0]); return 64; }
+  const int type = atoi(argv[1]), C = atoi(argv[2]), B = atoi(argv[3]), T = atoi(argv[4]), grid = atoi(argv[5]);
+  const int nrb = argc > 6 ? atoi(argv[6]) : 3;
+  const int ring = argc > 7 ? atoi(argv[7]) : 4;
+  const int thr = argc > 8 ? atoi(argv[8]) : (C == 32 ? 256 : 512);
+  const int la = argc > 9 ? atoi(argv[9]) : 0;
+#define RUN(CC, TH, NBB, RPP, TW) return run<CC, TH, NBB, RPP, TW>(type, B, T, grid, nrb, la)
+  if (type == 2) {
+    if (C == 32 && thr == 256 && ring == 4) RUN(32, 256, 4, 225, false);
+    if (C == 32 && thr == 256 && ring == 6) RUN(32, 256, 6, 225, false);
+    if (C == 64 && thr == 512 && ring == 4) RUN(64, 512, 4, 225, false);
+    if (C == 64 && thr == 512 && ring == 6) RUN(64, 512, 6, 225, false);
+    if (C == 64 && thr == 256 && ring == 6) return 64;   // 2 staging units per thread: not instantiated
+  } else {
+    if (C == 32 && thr == 256 && ring == 4) RUN(32, 256, 4, 249, true);
+    if (C == 32 && thr == 256 && ring == 6) RUN(32, 256, 6, 249, true);
+    if (C == 64 && thr == 512 && ring == 4) RUN(64, 512, 4, 249, true);
+    if (C == 64 && thr == 512 && ring == 6) RUN(64, 512, 6, 249, true);
+  }
+  return 64;
+}

@@ -9,10 +9,11 @@ from wetts_b200.hparams import builtin_config
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 CASES = ["v3_ragged", "v3_single", "v1_ragged", "v2_short"]
-# BASELINE.json configs[4] family (AISHELL-3 v1, 218 speakers, 128/80 phonemes) and configs[0] (Baker v1, the CLI
-# utterance, batch 1, CLI scales): pinned on the CPU with the other fixtures; on the GPU they run in their own
-# file (tests/test_zz_widecases_gpu.py) after everything else.
-WIDE_CASES = ["aishell3_long", "baker_v1_cli"]
+# BASELINE.json configs[4] family (AISHELL-3 v1, 218 speakers, 128/80 phonemes), configs[0] (Baker v1, the CLI
+# utterance, batch 1, CLI scales) and the benchmark's own route (multilingual v3 at Tx = 128, ragged 128/97/64: every
+# text-encoder / duration-predictor conv takes the tcgen05 kernel): pinned on the CPU with the other fixtures; on the
+# GPU they gate in tests/test_zz_widecases_gpu.py.
+WIDE_CASES = ["aishell3_long", "baker_v1_cli", "v3_tx128"]
 
 
 def load_case(name):

@@ -1,0 +1,69 @@
+"""CPU check of the f16-split fused MRF kernel SOURCE (wetts_b200/csrc/fused_mrf16_kernel.cuh) in the host CTA emulator.
+
+Same method as tests/test_fused_emu_cpu.py: the kernel contains no PTX, every primitive maps to tests/emu/emu_runtime.h
+(kind::f16 MMAs evaluated from the shared-memory descriptors, K = 16, fp16 operands), and the driver
+tests/emu/fused_mrf16_emu.cpp compares against an fp64 evaluation of ResBlock1 / ResBlock2 x nrb + the MRF mean
+(decoders.py:157-170, :205-214, :72-76); it exits non-zero above 2e-5 of rms or if a skipped tile was written."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+def _build(out, include_dir):
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    subprocess.run([gxx, "-O2", "-std=c++20", "-pthread", "-x", "c++", "-I", EMU, "-I", include_dir,
+                    os.path.join(EMU, "fused_mrf16_emu.cpp"), "-o", out], check=True, capture_output=True, text=True)
+    return out
+
+
+@pytest.fixture(scope="module")
+def emu_binary(tmp_path_factory):
+    return _build(str(tmp_path_factory.mktemp("emu16") / "fused_mrf16_emu"), os.path.join(ROOT, "wetts_b200", "csrc"))
+
+
+# (type, C, B, T, grid, nrb, ring, threads, length-aware): ResBlock2 (v3) and ResBlock1 (v1) stages, both widths, both
+# ring sizes, ragged last tile, single short tile, more CTAs than items, 1-3 resblocks, the length-aware item list
+CASES = [(2, 32, 2, 300, 2, 3, 4, 256, 0), (2, 32, 1, 76, 1, 3, 6, 256, 0), (2, 32, 2, 256, 5, 1, 6, 256, 0),
+         (2, 64, 2, 300, 2, 3, 6, 512, 0), (2, 64, 3, 320, 4, 2, 4, 512, 0), (2, 32, 4, 1000, 3, 3, 6, 256, 1),
+         (1, 32, 2, 300, 2, 3, 6, 256, 0), (1, 32, 1, 76, 1, 3, 4, 256, 0), (1, 64, 2, 300, 2, 3, 6, 512, 0),
+         (1, 32, 4, 700, 3, 3, 6, 256, 1)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fused_mrf16_kernel_in_emulator(emu_binary, case):
+    r = subprocess.run([emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rel=" in r.stdout
+
+
+# ---- the emulator must be able to FAIL on this kernel too
+MUTATIONS = {
+    # the epilogue reads TMEM without waiting for the accumulator barrier -> stale accumulators
+    "no_acc_wait": ("        mbar_wait(bar_acc, conv_count & 1);", "        // (mutation) no wait"),
+    # the small-term columns are added without the 2^-11 scale
+    "lo_scale_missing": ("vs[8 * g8 + e] * kF16LoInv", "vs[8 * g8 + e]"),
+    # ResBlock1's inner conv result lands in the X tile instead of T (the residual input is destroyed)
+    "inner_conv_overwrites_x": ("uint8_t* dst_tile = inner ? Tt : Xt;", "uint8_t* dst_tile = Xt;"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MUTATIONS))
+def test_emulator_detects_broken_mrf16_kernels(tmp_path, name):
+    csrc = os.path.join(ROOT, "wetts_b200", "csrc")
+    for f in ("fused_mrf16_kernel.cuh", "fused_mrf16_args.h", "tc_prims.cuh"):
+        shutil.copy(os.path.join(csrc, f), tmp_path / f)
+    old, new = MUTATIONS[name]
+    src = (tmp_path / "fused_mrf16_kernel.cuh").read_text()
+    assert src.count(old) == 1, f"mutation anchor for {name} not found exactly once"
+    (tmp_path / "fused_mrf16_kernel.cuh").write_text(src.replace(old, new))
+    out = _build(str(tmp_path / "emu_mut"), str(tmp_path))
+    args = ["1", "32", "2", "300", "2", "3", "6"] if name == "inner_conv_overwrites_x" else ["2", "32", "2", "300", "2", "3", "4"]
+    r = subprocess.run([out] + args, capture_output=True, text=True, timeout=900)
+    assert r.returncode != 0, "the emulator accepted a kernel with a known defect:\n" + r.stdout

@@ -4,6 +4,7 @@
 // operation is a CUDA kernel from conv_kernels.cu / misc_kernels.cu.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -24,7 +25,9 @@ static thread_local std::string g_err;
 // (wetts_vits_set_option), else the process-wide default (wetts_set_option).  Set by CHECK_READY.
 struct CallOpts {
   bool tc = true, fused = true, len_aware = false;
+  int fmt = 32;   // operand format of the fused stage kernels: 32 = 3xTF32 (kind::tf32), 16 = f16 split (kind::f16)
 };
+static std::atomic<int> g_tensor_format{32};
 static thread_local CallOpts g_call;
 
 static int fail(const char* fmt, ...) {
@@ -108,7 +111,7 @@ struct wetts_vits_s {
   std::map<std::string, Raw> raw;
   std::vector<void*> owned;
   // per-handle options: -1 = follow the process-wide option (wetts_set_option)
-  int opt_tc = -1, opt_fused = -1, opt_len_aware = 0;
+  int opt_tc = -1, opt_fused = -1, opt_len_aware = 0, opt_fmt = -1;
   unsigned long long launches_at_create = 0;
   int U = 1;
 
@@ -148,6 +151,7 @@ struct wetts_vits_s {
   };
   std::vector<ResBlock> rbs;
   std::vector<float*> fused_rb_w;  // per stage: packed weights of the fused MRF kernel (nullptr: per-layer path)
+  std::vector<void*> fused16_w;    // per stage: packed f16-split weights of fused_mrf16_kernel (nullptr: not eligible)
   float* conv_post_w = nullptr;
   int c_last = 0;
   float* emb_g = nullptr;
@@ -406,6 +410,11 @@ int wetts_set_option(const char* name, int value) {
     set_tensor_cores_enabled(value != 0);
     return 0;
   }
+  if (!strcmp(name, "tensor_format")) {
+    if (value != 16 && value != 32) return fail("tensor_format must be 16 (f16 split) or 32 (3xTF32)");
+    g_tensor_format.store(value);
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int wetts_get_option(const char* name, int* value) {
@@ -418,6 +427,10 @@ int wetts_get_option(const char* name, int* value) {
     *value = fused_resblock_enabled() ? 1 : 0;
     return 0;
   }
+  if (!strcmp(name, "tensor_format")) {
+    *value = g_tensor_format.load();
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int wetts_vits_set_option(wetts_vits_t h, const char* name, int value) {
@@ -425,7 +438,10 @@ int wetts_vits_set_option(wetts_vits_t h, const char* name, int value) {
   if (!strcmp(name, "tensor_cores")) h->opt_tc = value < 0 ? -1 : (value != 0);
   else if (!strcmp(name, "fused_resblock")) h->opt_fused = value < 0 ? -1 : (value != 0);
   else if (!strcmp(name, "length_aware")) h->opt_len_aware = value != 0;
-  else return fail("unknown option '%s'", name);
+  else if (!strcmp(name, "tensor_format")) {
+    if (value != 16 && value != 32 && value >= 0) return fail("tensor_format must be 16, 32 or -1 (process default)");
+    h->opt_fmt = value;
+  } else return fail("unknown option '%s'", name);
   return 0;
 }
 int wetts_vits_get_option(wetts_vits_t h, const char* name, int* value) {
@@ -433,6 +449,7 @@ int wetts_vits_get_option(wetts_vits_t h, const char* name, int* value) {
   if (!strcmp(name, "tensor_cores")) *value = h->opt_tc >= 0 ? h->opt_tc : (tensor_cores_enabled() ? 1 : 0);
   else if (!strcmp(name, "fused_resblock")) *value = h->opt_fused >= 0 ? h->opt_fused : (fused_resblock_enabled() ? 1 : 0);
   else if (!strcmp(name, "length_aware")) *value = h->opt_len_aware;
+  else if (!strcmp(name, "tensor_format")) *value = h->opt_fmt > 0 ? h->opt_fmt : g_tensor_format.load();
   else return fail("unknown option '%s'", name);
   return 0;
 }
@@ -632,6 +649,43 @@ int wetts_vits_finalize(wetts_vits_t h) {
         }
         h->rbs.push_back(rb);
       }
+      // f16-split fused MRF stage kernel (fused_mrf16_kernel.cuh): ResBlock1 and ResBlock2 stages with 32 / 64 channels
+      h->fused16_w.push_back(nullptr);
+      if (c.n_resblock_kernels <= kMrfMaxRb) {
+        const int nk = c.n_resblock_kernels;
+        const int nconv = (c.resblock_type == 1) ? 6 : 2;
+        int ks[kMrfMaxRb] = {0, 0, 0}, dil[kMrfMaxRb][kMrfMaxConv] = {};
+        bool ok = true;
+        size_t halfs = 0;
+        for (int j = 0; j < nk && ok; ++j) {
+          const auto& rb = h->rbs[(size_t)i * nk + j];
+          ks[j] = rb.k;
+          if (c.resblock_type == 1) {
+            ok = rb.dil.size() == 3 && rb.c1.size() == 3 && rb.c2.size() == 3;
+            for (int n = 0; n < 3 && ok; ++n) { dil[j][2 * n] = rb.dil[n]; dil[j][2 * n + 1] = 1; ok = rb.c1[n].b && rb.c2[n].b; }
+          } else {
+            ok = rb.dil.size() == 2 && rb.c1.size() == 2 && rb.c1[0].b && rb.c1[1].b;
+            if (ok) { dil[j][0] = rb.dil[0]; dil[j][1] = rb.dil[1]; }
+          }
+          halfs += (size_t)nconv * fused_mrf16_conv_halfs(ch, rb.k);
+        }
+        if (ok && fused_mrf16_supported(ch, c.resblock_type, nk, ks, dil, nconv)) {
+          uint16_t* fw;
+          if (h->dalloc(&fw, halfs + 64)) return 1;
+          size_t off = 0;
+          for (int j = 0; j < nk; ++j) {
+            const auto& rb = h->rbs[(size_t)i * nk + j];
+            for (int cc = 0; cc < nconv; ++cc) {
+              const Conv& cv = (c.resblock_type == 1) ? ((cc & 1) ? rb.c2[cc / 2] : rb.c1[cc / 2]) : rb.c1[cc];
+              launch_fused_mrf16_pack(cv.wraw, fw + off, ch, cv.K, 0);
+              off += fused_mrf16_conv_halfs(ch, cv.K);
+            }
+          }
+          h->fused16_w.back() = fw;
+          uint32_t smem_base = 0;
+          if (dyn_smem_offset(&smem_base, 0)) return fail("dynamic shared memory probe failed");
+        }
+      }
       // fused ResBlock2/MRF stage kernel (fused_rb_kernel.cuh) when the stage is eligible
       h->fused_rb_w.push_back(nullptr);
       if (c.resblock_type == 2 && c.n_resblock_kernels <= 3) {
@@ -684,7 +738,8 @@ int wetts_vits_finalize(wetts_vits_t h) {
   CUDA_OK(cudaSetDevice((h)->device));                                                        \
   g_call.tc = ((h)->opt_tc >= 0 ? (h)->opt_tc != 0 : tensor_cores_enabled());                 \
   g_call.fused = ((h)->opt_fused >= 0 ? (h)->opt_fused != 0 : fused_resblock_enabled());      \
-  g_call.len_aware = (h)->opt_len_aware != 0;
+  g_call.len_aware = (h)->opt_len_aware != 0;                                                 \
+  g_call.fmt = ((h)->opt_fmt > 0 ? (h)->opt_fmt : g_tensor_format.load());
 
 #define CHECK_LAUNCH()                                                                                   \
   do {                                                                                                   \
@@ -970,6 +1025,7 @@ int wetts_flow_reverse(wetts_vits_t h, float* z, const int64_t* y_lengths, const
 // ------------------------------------------------------------------ generator
 struct GenWs {
   float *cvec, *x[2], *xu, *r, *t;
+  void* item_map;   // length-aware mode: work-item list of the fused stage being launched
 };
 static size_t gen_layout(wetts_vits_t h, int B, int T, Arena& A, GenWs* w) {
   const wetts_vits_config& c = h->cfg;
@@ -987,6 +1043,7 @@ static size_t gen_layout(wetts_vits_t h, int B, int T, Arena& A, GenWs* w) {
   w->xu = A.take<float>(mx);
   w->r = A.take<float>(mx);
   w->t = c.resblock_type == 1 ? A.take<float>(mx) : nullptr;
+  w->item_map = A.take<char>(mrf_item_map_bytes(B, (int)len));
   return A.off;
 }
 size_t wetts_generator_workspace_bytes(wetts_vits_t h, int B, int T) {
@@ -1051,6 +1108,26 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
     const int ch = up.Cout;
     const long long bs = (long long)ch * len;
     float* acc = w.x[cur ^ 1];
+    if (h->fused16_w[i] && g_call.tc && g_call.fused && g_call.fmt == 16 && (len & 3) == 0) {
+      FusedMrfArgs fa;
+      fa.in = w.xu; fa.out = acc; fa.w = h->fused16_w[i];
+      fa.B = B; fa.T = len; fa.nrb = nk; fa.slope = 0.1f; fa.div = (float)nk;
+      fa.type = c.resblock_type; fa.nconv = (c.resblock_type == 1) ? 6 : 2;
+      for (int j = 0; j < nk; ++j) {
+        const auto& rb = h->rbs[i * nk + j];
+        fa.k[j] = rb.k;
+        for (int cc = 0; cc < fa.nconv; ++cc) {
+          const Conv& cv = (c.resblock_type == 1) ? ((cc & 1) ? rb.c2[cc / 2] : rb.c1[cc / 2]) : rb.c1[cc];
+          fa.dil[j][cc] = (c.resblock_type == 1) ? ((cc & 1) ? 1 : rb.dil[cc / 2]) : rb.dil[cc];
+          fa.bias[j][cc] = cv.b;
+        }
+      }
+      if (g_call.len_aware && y_lengths)   // frames beyond len + 16 (> the generator's receptive field) are not computed
+        launch_mrf_item_map((const long long*)y_lengths, B, len, len / T, 16, w.item_map, &fa.item_map, &fa.n_items_dev, s);
+      if (launch_fused_mrf16(ch, fa, s)) return fail("fused MRF (f16) launch failed");
+      cur ^= 1;
+      continue;
+    }
     if (h->fused_rb_w[i] && g_call.tc && g_call.fused && (len & 3) == 0) {   // 16 B row loads
       FusedRbArgs fa;
       fa.in = w.xu; fa.out = acc; fa.w = h->fused_rb_w[i];

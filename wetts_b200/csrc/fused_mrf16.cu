@@ -1,0 +1,180 @@
+// Launch side of the f16-split fused MRF stage kernel (fused_mrf16_kernel.cuh): weight packing into the per-item
+// chunk sequence, eligibility checks, persistent-grid launch, optional length-aware tile list.
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "fused_mrf16_kernel.cuh"
+#include "kernels.cuh"
+
+namespace wetts {
+namespace {
+
+// dst (halfs) [tap][32-channel slice][4 k-groups][hi | lo'][n][8] <- folded weight src[co][ci][tap]
+__global__ void fused_mrf16_pack_kernel(const float* __restrict__ src, uint16_t* __restrict__ dst, int C, int K) {
+  const long long total = (long long)K * C * C * 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const FusedMrfPackIdx ix = fused_mrf16_pack_index(i, C);
+    const float w = src[((long long)ix.co * C + ix.ci) * K + ix.tap];
+    uint32_t hi2, lo2;
+    tc::f16_split2(w, 0.f, hi2, lo2);
+    dst[i] = (uint16_t)((ix.hl ? lo2 : hi2) & 0xFFFFu);
+  }
+}
+
+// Work-item list of the length-aware mode: utterance b contributes tiles(b) = ceil(min(T, (len[b] + margin) * rate) / 128)
+// items (at least one), in (b, tile) order.  One block: a serial prefix over B (a few thousand at most), then every
+// thread fills the segments of its utterances.
+__global__ void mrf_item_map_kernel(const long long* __restrict__ lengths, int B, int T, int rate, int margin,
+                                    int2_t* __restrict__ item_map, int* __restrict__ n_items, int* __restrict__ prefix) {
+  auto tiles = [&](int b) {
+    long long n = (lengths[b] + margin) * (long long)rate;
+    if (n > T) n = T;
+    if (n < 1) n = 1;
+    return (int)((n + 127) / 128);
+  };
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 0; b < B; ++b) { prefix[b] = acc; acc += tiles(b); }
+    prefix[B] = acc;
+    *n_items = acc;
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const int first = prefix[b], n = prefix[b + 1] - first;
+    for (int i = 0; i < n; ++i) item_map[first + i] = int2_t{b, i * 128};
+  }
+}
+
+}  // namespace
+
+bool fused_mrf16_supported(int C, int type, int nrb, const int* k, const int (*dil)[kMrfMaxConv], int nconv) {
+  if (C != 32 && C != 64) return false;
+  if (nrb < 1 || nrb > kMrfMaxRb) return false;
+  if (!((type == 2 && nconv == 2) || (type == 1 && nconv == 6))) return false;
+  const int rp = (type == 1) ? 249 : 225;
+  for (int j = 0; j < nrb; ++j) {
+    if (k[j] < 1 || (k[j] & 1) == 0) return false;
+    int H = 0;
+    for (int c = 0; c < nconv; ++c) {
+      if (dil[j][c] < 1) return false;
+      H += dil[j][c] * (k[j] - 1) / 2;
+    }
+    if (type == 1)
+      for (int c = 1; c < nconv; c += 2)
+        if (dil[j][c] != 1) return false;                      // decoders.py:118-140: convs2 have dilation 1
+    const int Hp = (H + 3) & ~3;
+    if (128 + 2 * Hp > rp - 1) return false;                    // rows of the activation tile (QMAX quads)
+    const int h0 = dil[j][0] * (k[j] - 1) / 2;
+    if (128 + 2 * (H - h0) > 256) return false;                 // two 128-row blocks must cover the first conv's output
+  }
+  return true;
+}
+
+void launch_fused_mrf16_pack(const float* w_folded, void* dst, int C, int K, cudaStream_t s) {
+  const long long total = (long long)fused_mrf16_conv_halfs(C, K);
+  const int blocks = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+  fused_mrf16_pack_kernel<<<blocks, 256, 0, s>>>(w_folded, reinterpret_cast<uint16_t*>(dst), C, K);
+  count_launch();
+}
+
+size_t mrf_item_map_bytes(int B, int T) {
+  return sizeof(int2_t) * (size_t)B * ((size_t)(T + 127) / 128) + sizeof(int) * ((size_t)B + 2) + 64;
+}
+void launch_mrf_item_map(const long long* lengths, int B, int T, int rate, int margin, void* scratch, const int2_t** item_map,
+                         const int** n_items_dev, cudaStream_t s) {
+  int2_t* map = reinterpret_cast<int2_t*>(scratch);
+  int* n_items = reinterpret_cast<int*>(map + (size_t)B * ((size_t)(T + 127) / 128));
+  int* prefix = n_items + 1;
+  mrf_item_map_kernel<<<1, 256, 0, s>>>(lengths, B, T, rate, margin, map, n_items, prefix);
+  count_launch();
+  *item_map = map;
+  *n_items_dev = n_items;
+}
+
+template <int C, int THREADS, int MINB, int NB, int RP, bool TWO, bool PROFILE>
+static int launch_variant(const FusedMrfArgs& a, int grid, size_t smem, cudaStream_t s) {
+  auto kern = fused_mrf16_kernel<C, THREADS, MINB, NB, RP, TWO, PROFILE>;
+  static DynSmemAttr attr;
+  if (attr.ensure((const void*)kern, smem) != cudaSuccess) return 1;
+  kern<<<grid, THREADS, smem, s>>>(a);
+  count_launch();
+  return 0;
+}
+
+// CTAs per SM: the accumulators are reused by every conv (4N TMEM columns) and the f16 tiles are half the size of the
+// tf32 ones, so the ResBlock2 kernels fit 3 (C = 32) / 2... CTAs; co-resident CTAs overlap one CTA's SIMT phases with
+// another's MMAs.  WETTS_MRF16_CTAS overrides (experiments).
+static int ctas_per_sm(int C, int type) {
+  static const int forced = getenv("WETTS_MRF16_CTAS") ? atoi(getenv("WETTS_MRF16_CTAS")) : 0;
+  if (forced > 0) return forced;
+  if (C == 32) return type == 2 ? 3 : 2;
+  return 1;
+}
+
+template <bool PROFILE>
+static int launch_any(int C, int type, int ring, int per_sm, const FusedMrfArgs& a, int grid, size_t smem, cudaStream_t s) {
+#define V(CC, TH, MB, NBB, RPP, TW) launch_variant<CC, TH, MB, NBB, RPP, TW, PROFILE>(a, grid, smem, s)
+  if (type == 2 && C == 32) {
+    if (per_sm >= 3) return ring == 6 ? V(32, 256, 3, 6, 225, false) : V(32, 256, 3, 4, 225, false);
+    return ring == 6 ? V(32, 256, 2, 6, 225, false) : V(32, 256, 2, 4, 225, false);
+  }
+  if (type == 2 && C == 64) return ring == 6 ? V(64, 512, 1, 6, 225, false) : V(64, 512, 1, 4, 225, false);
+  if (type == 1 && C == 32) return ring == 6 ? V(32, 256, 2, 6, 249, true) : V(32, 256, 2, 4, 249, true);
+  if (type == 1 && C == 64) return ring == 6 ? V(64, 512, 1, 6, 249, true) : V(64, 512, 1, 4, 249, true);
+#undef V
+  return 1;
+}
+
+static int launch_profiled(int C, int type, int ring, int per_sm, FusedMrfArgs a, int grid, size_t smem, long long items,
+                           cudaStream_t s) {
+  static const char* names[kMrfProfPhases] = {"stage", "sync", "conv issue|prefetch", "acc wait", "epilogue", "sync", "out",
+                                              "[full-wait]", "loop", "-", "-", "-"};
+  const size_t n = (size_t)grid * 2 * kMrfProfPhases;
+  long long* d = nullptr;
+  if (cudaMalloc(&d, n * sizeof(long long)) != cudaSuccess) return 1;
+  cudaMemsetAsync(d, 0, n * sizeof(long long), s);
+  a.prof = d;
+  if (launch_any<true>(C, type, ring, per_sm, a, grid, smem, s)) return 1;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return 1;
+  std::vector<long long> h(n);
+  cudaMemcpy(h.data(), d, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  const double per_cta_items = (double)items / grid;
+  fprintf(stderr, "[fused_mrf16 profile] type=%d C=%d ring=%d ctas/sm=%d B=%d T=%d grid=%d items/CTA=%.1f  (cycles per item, mean over CTAs)\n",
+          type, C, ring, per_sm, a.B, a.T, grid, per_cta_items);
+  for (int who = 0; who < 2; ++who) {
+    double tot = 0;
+    fprintf(stderr, "  %s:", who ? "thread 32 (producer warp)" : "thread 0 (MMA issuer)   ");
+    for (int i = 0; i < 9; ++i) {
+      double sum = 0;
+      for (int b = 0; b < grid; ++b) sum += (double)h[((size_t)b * 2 + who) * kMrfProfPhases + i];
+      const double v = sum / grid / per_cta_items;
+      if (i != 7) tot += v;
+      fprintf(stderr, " %s=%.0f", names[i], v);
+    }
+    fprintf(stderr, " | total=%.0f\n", tot);
+  }
+  return 0;
+}
+
+int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
+  if ((a.T & 3) != 0 || (((uintptr_t)a.in | (uintptr_t)a.out | (uintptr_t)a.w) & 15) != 0) return 1;   // 16 B loads / bulk copies
+  fused_mrf16_finalize_args(a, C);
+  if (dyn_smem_offset(&a.smem_off, s)) return 1;
+  const int n_sm = current_device_sm_count();
+  if (n_sm <= 0) return 1;
+  const char* force = getenv("WETTS_FUSED_RB_RING");
+  const int ring = force ? atoi(force) : fused_mrf16_ring_slots(a.nq);
+  if (ring != 4 && !(ring == 6 && a.nq % 6 == 0)) return 1;
+  const int rp = (a.type == 1) ? 249 : 225;
+  const size_t smem = fused_mrf16_smem_bytes(C, ring, rp, a.type == 1 ? 2 : 1);
+  const long long items = (long long)a.B * ((a.T + 127) / 128);   // upper bound in the length-aware mode
+  const int per_sm = ctas_per_sm(C, a.type);
+  const int grid = (int)(items < (long long)per_sm * n_sm ? items : (long long)per_sm * n_sm);
+  if (getenv("WETTS_FUSED_RB_PROFILE")) return launch_profiled(C, a.type, ring, per_sm, a, grid, smem, items, s);
+  return launch_any<false>(C, a.type, ring, per_sm, a, grid, smem, s);
+}
+
+}  // namespace wetts

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fused_mrf16_args.h"
 #include "fused_rb_args.h"
 
 namespace wetts {
@@ -94,6 +95,15 @@ void launch_fused_rb_pack(const float* w_folded /*[C][C][K]*/, float* dst, int C
 int launch_fused_rb(int C, FusedRbArgs a, cudaStream_t s);   // fills Rp / nq; returns 0 on success
 void set_fused_resblock_enabled(bool on);
 bool fused_resblock_enabled();
+
+// f16-split fused MRF stage (fused_mrf16.cu): ResBlock1 and ResBlock2 stages with C in {32, 64}
+bool fused_mrf16_supported(int C, int type, int nrb, const int* k, const int (*dil)[kMrfMaxConv], int nconv);
+void launch_fused_mrf16_pack(const float* w_folded /*[C][C][K]*/, void* dst, int C, int K, cudaStream_t s);
+int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s);
+// length-aware work-item list of a stage (samples per frame `rate`, `margin` frames beyond each utterance's length)
+size_t mrf_item_map_bytes(int B, int T);
+void launch_mrf_item_map(const long long* lengths, int B, int T, int rate, int margin, void* scratch, const int2_t** item_map,
+                         const int** n_items_dev, cudaStream_t s);
 
 struct ConvTArgs {
   const float* in = nullptr;  // [B][Cin][T]

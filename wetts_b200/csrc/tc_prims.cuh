@@ -33,6 +33,7 @@ WETTS_DEVICE float ldg(const float* p) { return __ldg(p); }
 WETTS_DEVICE long long clock_now() { return clock64(); }
 WETTS_DEVICE void trap_now() { __trap(); }
 WETTS_DEVICE float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+WETTS_DEVICE int ldg_i32(const int* p) { return __ldg(p); }
 
 WETTS_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -146,6 +147,18 @@ WETTS_DEVICE void tc_mma_f16_1(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t
       "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// f16 form of tc_mma_tf32_split2 (K = 16 channels per MMA): D[:, 0:2N] (+)= A_hi * [B_hi | B_lo'],  D[:, N:2N] += A_lo' * B_hi
+WETTS_DEVICE void tc_mma_f16_split2(uint32_t d_tmem, uint32_t d_tmem_small, uint64_t a_hi, uint64_t a_lo, uint64_t b_hilo,
+                                    uint32_t idesc_2n, uint32_t idesc_n, uint32_t accumulate_first) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %7, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %4, %5, pa;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%1], %3, %4, %6, 1;\n\t}" ::"r"(d_tmem),
+      "r"(d_tmem_small), "l"(a_hi), "l"(a_lo), "l"(b_hilo), "r"(idesc_2n), "r"(idesc_n), "r"(accumulate_first)
+      : "memory");
+}
 // A value every lane of the warp holds anyway, routed through a shuffle so that the compiler can PROVE it
 // warp-uniform: descriptor arithmetic then stays in uniform registers (UIADD3/UMOV feeding UTCHMMA directly).
 // Without this every tcgen05.mma operand takes an R2UR round trip (~90 cycles per MMA measured, see
@@ -199,6 +212,20 @@ WETTS_DEVICE float tf32_rna(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
+// two fp32 -> packed fp16 pair (round to nearest even, saturating to +-65504 instead of inf); element 0 in the low half
+WETTS_DEVICE uint32_t f16x2_pack(float lo_elem, float hi_elem) {
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem));
+  return d;
+}
+WETTS_DEVICE void f16x2_unpack(uint32_t v, float& lo_elem, float& hi_elem) {
+  asm("{\n\t.reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "cvt.f32.f16 %0, l;\n\t"
+      "cvt.f32.f16 %1, h;\n\t}"
+      : "=f"(lo_elem), "=f"(hi_elem)
+      : "r"(v));
+}
 
 }  // namespace tc
 }  // namespace wetts
@@ -206,6 +233,25 @@ WETTS_DEVICE float tf32_rna(float x) {
 
 namespace wetts {
 namespace tc {
+
+// fp32 -> two fp16 operands with the same 22 significand bits as the 3xTF32 split:  x ~ hi + lo' * 2^-11,
+// hi = f16(x), lo' = f16((x - hi) * 2^11).  The lo' parts of BOTH operands carry the 2^11 scale, so the two small
+// products (hi*lo', lo'*hi) accumulate in their own accumulator columns and are scaled by 2^-11 once, in the
+// epilogue.  |x| must stay below 65504 (saturating conversion; activations of this model family are O(10)).
+constexpr float kF16LoScale = 2048.0f, kF16LoInv = 1.0f / 2048.0f;
+WETTS_DEVICE void f16_split2(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+  hi2 = f16x2_pack(a, b);
+  float ha, hb;
+  f16x2_unpack(hi2, ha, hb);
+  lo2 = f16x2_pack((a - ha) * kF16LoScale, (b - hb) * kF16LoScale);
+}
+WETTS_DEVICE void f16_join2(uint32_t hi2, uint32_t lo2, float& a, float& b) {
+  float ha, hb, la, lb;
+  f16x2_unpack(hi2, ha, hb);
+  f16x2_unpack(lo2, la, lb);
+  a = ha + la * kF16LoInv;
+  b = hb + lb * kF16LoInv;
+}
 
 // shared-memory matrix descriptor: K-major, no swizzle (UMMA SmemDescriptor, version 1).
 // Element (row r, k) of the operand lives at start + (k/4)*LBO + (r/8)*SBO + (r%8)*16 + (k%4)*4.
