@@ -24,6 +24,6 @@ except Exception as e:
 PY
 done
 WETTS_FUSED_RB_PROFILE=1 timeout 200 python bench.py --steps 1 --warmup 1 --no-cpu --tensor-format 16 > /dev/null 2> gpurun_out/r2_prof16.log; grep -A2 "fused_mrf16 profile" gpurun_out/r2_prof16.log | tail -9
-for ctas in 2 4; do
+for ctas in 2; do
   WETTS_MRF16_CTAS=$ctas timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu --tensor-format 16 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('mrf16 ctas/sm(C=32)=$ctas ms/step', round(d['ms_per_step'],2), 'gen', round(d['roofline']['ms'],2))"
 done
