@@ -11,10 +11,11 @@ from wetts_b200.dist import plan_shards
 
 
 class StubNet:
-    """o[b,0,n] = sum(ids[b,:len]) + sid[b] + n/1000 for n < 2*len*U; y_lengths = 2*len."""
+    """o[b,0,n] = sum(ids[b,:len]) + sid[b] + n/1000 (+ noise_z[b,0,n // U] when given) for n < 2*len*U;
+    y_lengths = 2*len."""
     U = 4
 
-    def infer(self, x, x_lengths, sid=None, **kw):
+    def infer(self, x, x_lengths, sid=None, noise_z=None, **kw):
         B, Tx = x.shape
         ylen = 2 * x_lengths
         Ty = int(ylen.max())
@@ -22,6 +23,8 @@ class StubNet:
         m = (torch.arange(Tx)[None, :] < x_lengths[:, None])
         base = (x * m).sum(dim=1).float() + (0 if sid is None else sid.float())
         o = base[:, None, None] + torch.arange(Ty * self.U).float()[None, None, :] / 1000.0
+        if noise_z is not None:   # per-utterance injected noise must follow its utterance to whichever rank gets it
+            o = o + noise_z[:, :1, :Ty].repeat_interleave(self.U, dim=2)
         return o, None, y_mask, None
 
 
@@ -44,10 +47,11 @@ def _worker(rank, world, port, ret):
     x = torch.randint(1, 50, (B, Tx), generator=gen) * (torch.arange(Tx)[None, :] < lens[:, None])
     sid = torch.randint(0, 3, (B,), generator=gen)
     net = StubNet()
+    noise_z = torch.randn(B, 3, 2 * Tx, generator=gen)
     out = sharded_infer(net, x if rank == 0 else None, lens if rank == 0 else None, sid if rank == 0 else None,
-                        torch.device("cpu"), hop_upsample=StubNet.U)
+                        torch.device("cpu"), hop_upsample=StubNet.U, noise_z=noise_z if rank == 0 else None)
     if rank == 0:
-        ref, _, ym, _ = net.infer(x, lens, sid)
+        ref, _, ym, _ = net.infer(x, lens, sid, noise_z=noise_z)
         ok = len(out) == B
         for i in range(B):
             n = int(ym[i].sum()) * StubNet.U
