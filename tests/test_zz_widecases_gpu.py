@@ -23,11 +23,15 @@ BLOCK_TOL = 1e-4
 E2E_TOL = 1e-3
 
 
+@pytest.mark.parametrize("fmt", [32, 16])
 @pytest.mark.parametrize("name", WIDE_CASES)
-def test_wide_fixture_end_to_end_and_blocks(name):
+def test_wide_fixture_end_to_end_and_blocks(name, fmt):
+    """fmt = operand format of the tensor-pipe kernels: 32 = 3xTF32, 16 = f16 split (both must hold the same bounds)"""
     import wetts_b200
     hps, sd, g, t = load_case(name)
     net = wetts_b200.build_model(hps, int(g["n_vocab"]), int(g["n_speakers"]), sd, "cuda")
+    net.set_option("tensor_format", fmt)
+    name = f"{name}[fmt{fmt}]"
     dev = net.device
     ns, ls, nsw = [float(v) for v in g["scales"]]
     o, attn, y_mask, (z, z_p, m_p, logs_p) = net.infer(
@@ -66,13 +70,15 @@ def test_wide_fixture_end_to_end_and_blocks(name):
     assert e_g < BLOCK_TOL * 3
 
 
+@pytest.mark.parametrize("fmt", [32, 16])
 @pytest.mark.parametrize("name", WIDE_CASES)
-def test_own_durations_on_the_tensor_core_route_are_exact(name):
+def test_own_durations_on_the_tensor_core_route_are_exact(name, fmt):
     """No teacher forcing: ceil(exp(logw) * length_scale) from the GPU's own text encoder + duration predictor (tcgen05
     route at Tx >= 64) must land on the reference's integers -- the numerator of the benchmark's metric."""
     import wetts_b200
     hps, sd, g, t = load_case(name)
     net = wetts_b200.build_model(hps, int(g["n_vocab"]), int(g["n_speakers"]), sd, "cuda")
+    net.set_option("tensor_format", fmt)
     ns, ls, nsw = [float(v) for v in g["scales"]]
     net.infer(t["x"], t["x_lengths"], t["sid"], noise_scale=ns, length_scale=ls, noise_scale_w=nsw,
               noise_w=t["noise_w"], noise_z=t["noise_z"], return_attn=False)

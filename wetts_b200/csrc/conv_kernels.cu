@@ -424,7 +424,8 @@ void launch_cond_vector(const float* g, const float* w, const float* bias, float
 }
 
 void launch_conv1d(const ConvArgs& a, cudaStream_t s) {
-  if (a.wtc && a.T >= 64 && a.dil == a.tc.dil && a.use_tc) launch_conv1d_tc(a, s);
+  if (a.wtc16 && a.fmt == 16 && a.T >= 64 && a.dil == a.tc16.dil && a.use_tc) launch_conv1d_tc16(a, s);
+  else if (a.wtc && a.T >= 64 && a.dil == a.tc.dil && a.use_tc) launch_conv1d_tc(a, s);
   else launch_conv1d_simt(a, s);
 }
 

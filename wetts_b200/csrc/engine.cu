@@ -60,8 +60,9 @@ struct Conv {
   float* w = nullptr;    // SIMT layout [Cin][K][CoutPad]
   float* b = nullptr;
   float* wtc = nullptr;  // tcgen05 layout (tc_conv_kernel.cu), hi/lo tf32 split
+  uint16_t* wtc16 = nullptr;  // tcgen05 layout of the f16 split (tc16_conv_kernel.cu)
   const float* wraw = nullptr;  // folded source weight [Cout][Cin][K] (before any channel map)
-  TcPlan tc;
+  TcPlan tc, tc16;
   int Cin = 0, Cout = 0, CoutPad = 0, K = 1;
 };
 struct ConvT {
@@ -233,6 +234,16 @@ struct wetts_vits_s {
       if (dalloc(&c->wtc, c->tc.packed_floats)) return 1;
       launch_pack_conv_tc(w.d, c->wtc, d_co, d_ci, c->Cout, c->Cin, K, src_cin, c->tc, 0);
     }
+    c->wtc16 = nullptr;
+    if (tc_dil > 0 && tc16_conv_plan(c->Cin, c->Cout, K, tc_dil, &c->tc16)) {
+      if (getenv("WETTS_DEBUG_PLAN"))
+        fprintf(stderr, "[tc16 plan] Cin=%d Cout=%d K=%d dil=%d -> mode=%d N=%d n_tiles=%d KC=%d chunks=%d MB=%d G=%d abuf=%d bbuf=%d smem=%zu\n",
+                c->Cin, c->Cout, K, tc_dil, c->tc16.mode, c->tc16.N, c->tc16.n_tiles, c->tc16.KC, c->tc16.n_chunks, c->tc16.MB,
+                c->tc16.G, c->tc16.n_abuf, c->tc16.n_bbuf,
+                tc16_conv_smem_bytes(K, tc_dil, c->tc16.N, c->tc16.KC, c->tc16.MB, c->tc16.n_abuf, c->tc16.n_bbuf));
+      if (dalloc(&c->wtc16, c->tc16.packed_floats + 64)) return 1;
+      launch_pack_conv_tc16(w.d, c->wtc16, d_co, d_ci, c->Cout, c->Cin, K, src_cin, c->tc16, 0);
+    }
     return 0;
   }
   int make_conv(const std::string& prefix, Conv* c, bool bias = true, std::vector<int> co_map = {},
@@ -279,6 +290,9 @@ static ConvArgs conv_args(const Conv& c, const float* in, long long in_bs, int i
   ConvArgs a;
   a.wtc = c.wtc;
   a.tc = c.tc;
+  a.wtc16 = c.wtc16;
+  a.tc16 = c.tc16;
+  a.fmt = g_call.fmt;
   a.in = in;
   a.in_bs = in_bs;
   a.in_cs = in_cs;
@@ -1091,7 +1105,8 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
     ta.in = w.x[cur]; ta.w = up.w; ta.bias = up.b; ta.out = w.xu; ta.B = B; ta.Cin = up.Cin; ta.Cout = up.Cout;
     ta.CoutPad = up.CoutPad; ta.T = len; ta.u = up.u; ta.ntaps = up.ntaps; ta.pad = up.pad; ta.pre_slope = 0.1f;
     // polyphase form needs the tcgen05 kernel (EPI_CONVT / in_T exist only there) and exactly two taps per phase
-    if (up.as_conv.wtc && g_call.tc && up.ntaps == 2 && len + up.ntaps - 1 >= 64 && up.as_conv.tc.dil == 1) {
+    const bool up16 = up.as_conv.wtc16 && g_call.fmt == 16;
+    if ((up.as_conv.wtc || up16) && g_call.tc && up.ntaps == 2 && len + up.ntaps - 1 >= 64) {
       // polyphase form on the tensor pipe: a 2-tap conv over the input frames with Cout*u packed channels
       ConvArgs ca = conv_args(up.as_conv, w.x[cur], (long long)up.Cin * len, len, B, len, 1);
       ca.T = len + up.ntaps - 1;       // frames q = 0 .. len + ntaps - 2 reach output samples
@@ -1100,7 +1115,7 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
       ca.pre_act = 1; ca.pre_slope = 0.1f;
       ca.ep.mode = EPI_CONVT; ca.ep.out = w.xu; ca.ep.out_bs = (long long)up.Cout * len * up.u;
       ca.ep.up_u = up.u; ca.ep.up_pad = up.pad; ca.ep.out_T = (long long)len * up.u;
-      launch_conv1d_tc(ca, s);
+      if (up16) launch_conv1d_tc16(ca, s); else launch_conv1d_tc(ca, s);
     } else {
       launch_conv_transpose1d(ta, s);
     }

@@ -50,8 +50,11 @@ struct TcPlan {
 };
 
 struct ConvArgs {
-  const float* wtc = nullptr;  // tensor-core packed weights (nullptr: SIMT path only)
+  const float* wtc = nullptr;  // tensor-core packed weights, 3xTF32 layout (nullptr: not eligible)
   TcPlan tc;
+  const void* wtc16 = nullptr; // tensor-core packed weights, f16-split layout (nullptr: not eligible)
+  TcPlan tc16;
+  int fmt = 32;               // operand format to use when both layouts exist: 16 = f16 split, 32 = 3xTF32
   const float* in = nullptr;  // [B][Cin][T] view: element (b,ci,t) at in + b*in_bs + ci*in_cs + t
   long long in_bs = 0;
   int in_cs = 0;
@@ -85,6 +88,12 @@ size_t tc_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_abuf, int
 void launch_pack_conv_tc(const float* src, float* dst, const int* co_map, const int* ci_map, int Cout, int Cin, int K,
                          int src_cin, const TcPlan& pl, cudaStream_t s);
 void launch_conv1d_tc(const ConvArgs& a, cudaStream_t s);
+// f16-split twin (tc16_conv_kernel.cu); plan->packed_floats counts HALFS for this format
+bool tc16_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan);
+size_t tc16_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_abuf, int n_bbuf);
+void launch_pack_conv_tc16(const float* src, void* dst, const int* co_map, const int* ci_map, int Cout, int Cin, int K,
+                           int src_cin, const TcPlan& pl, cudaStream_t s);
+void launch_conv1d_tc16(const ConvArgs& a, cudaStream_t s);
 void set_tensor_cores_enabled(bool on);
 bool tensor_cores_enabled();
 
