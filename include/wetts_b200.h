@@ -201,6 +201,14 @@ int wetts_vits_forward_decoder(wetts_vits_t h, const float* z_blc, const int64_t
 int wetts_audio_to_int16(const float* audio, const int64_t* lengths, int B, int64_t L, int mode, float* peak_scratch,
                          int16_t* out, void* stream);
 
+/* Watchdog.  The tensor-pipe kernels synchronise through mbarriers; a wait that does not complete within 2^24 polls
+ * (a pipeline bug, never normal operation) records the reason in a host-visible word and traps, so a defect shows up
+ * as a failed launch within a fraction of a second instead of a hung GPU.  As after any device-side trap the CUDA
+ * context is lost; every later call on it fails.  This call (optionally after synchronising `stream`) returns non-zero
+ * with "pipeline watchdog fired" in wetts_last_error() when that was the cause, so a serving process can tell a
+ * kernel defect from other launch failures before it restarts. */
+int wetts_vits_check_fault(wetts_vits_t h, void* stream, int synchronize);
+
 /* Counters for benchmarks: number of kernels this library has launched on behalf
  * of the handle since creation (monotonic). */
 uint64_t wetts_vits_launch_count(wetts_vits_t h);

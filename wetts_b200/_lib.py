@@ -59,6 +59,7 @@ PROTOTYPES = {
     "wetts_vits_decoder_workspace_bytes": (_SZ, [_P, _I, _I]),
     "wetts_vits_forward_decoder": (_I, [_P, _P, _P, _I, _I, _P, _P, _SZ, _P]),
     "wetts_audio_to_int16": (_I, [_P, _P, _I, _I64, _I, _P, _P, _P]),
+    "wetts_vits_check_fault": (_I, [_P, _P, _I]),
     "wetts_vits_launch_count": (C.c_uint64, [_P]),
 }
 

@@ -28,6 +28,34 @@ struct CallOpts {
   int fmt = 32;   // operand format of the fused stage kernels: 32 = 3xTF32 (kind::tf32), 16 = f16 split (kind::f16)
 };
 static std::atomic<int> g_tensor_format{32};
+
+// Host-visible fault word of the device-side soft watchdog (tc_prims.cuh mbar_wait): one mapped pinned word per
+// process, installed on every device a handle is created on.
+static std::atomic<unsigned int*> g_fault_word{nullptr};
+static int ensure_fault_word(int device) {
+  unsigned int* w = g_fault_word.load();
+  if (!w) {
+    unsigned int* fresh = nullptr;
+    if (cudaHostAlloc((void**)&fresh, 64, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return 1;
+    *fresh = 0;
+    unsigned int* expected = nullptr;
+    if (g_fault_word.compare_exchange_strong(expected, fresh)) w = fresh;
+    else { cudaFreeHost(fresh); w = expected; }
+  }
+  (void)device;
+  unsigned int* dptr = nullptr;
+  if (cudaHostGetDevicePointer((void**)&dptr, w, 0) != cudaSuccess) return 1;
+  return tc_conv_install_fault_word(dptr) | tc16_conv_install_fault_word(dptr) | fused_rb_install_fault_word(dptr) |
+         fused_mrf16_install_fault_word(dptr);
+}
+// nonzero (and the word cleared) if a device-side pipeline wait timed out since the last check
+static unsigned int take_fault() {
+  unsigned int* w = g_fault_word.load();
+  if (!w) return 0;
+  const unsigned int v = *(volatile unsigned int*)w;
+  if (v) *(volatile unsigned int*)w = 0;
+  return v;
+}
 static thread_local CallOpts g_call;
 
 static int fail(const char* fmt, ...) {
@@ -40,10 +68,13 @@ static int fail(const char* fmt, ...) {
   return 1;
 }
 
+static unsigned int take_fault();
 #define CUDA_OK(expr)                                                                        \
   do {                                                                                       \
     cudaError_t _e = (expr);                                                                 \
-    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    if (_e != cudaSuccess)                                                                   \
+      return fail("%s failed: %s%s (%s:%d)", #expr, cudaGetErrorString(_e),                  \
+                  take_fault() ? " -- device pipeline watchdog fired (an mbarrier wait timed out)" : "", __FILE__, __LINE__); \
   } while (0)
 
 struct Raw {
@@ -399,6 +430,10 @@ int wetts_vits_create(const wetts_vits_config* cfg, int device, wetts_vits_t* ou
   h->device = device;
   h->U = U;
   h->launches_at_create = kernel_launch_counter();
+  if (ensure_fault_word(device)) {
+    delete h;
+    return fail("could not install the watchdog fault word");
+  }
   *out = h;
   return 0;
 }
@@ -475,6 +510,15 @@ int wetts_audio_to_int16(const float* audio, const int64_t* lengths, int B, int6
   launch_audio_to_int16(audio, (const long long*)lengths, B, (long long)L, mode, peak_scratch, (short*)out,
                         (cudaStream_t)stream);
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int wetts_vits_check_fault(wetts_vits_t h, void* stream, int synchronize) {
+  if (!h) return fail("null handle");
+  CUDA_OK(cudaSetDevice(h->device));
+  if (synchronize) CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  CUDA_OK(cudaGetLastError());
+  if (take_fault()) return fail("device pipeline watchdog fired (an mbarrier wait timed out)");
   return 0;
 }
 

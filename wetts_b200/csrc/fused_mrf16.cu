@@ -177,4 +177,6 @@ int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
   return launch_any<false>(C, a.type, ring, per_sm, a, grid, smem, s);
 }
 
+int fused_mrf16_install_fault_word(unsigned int* word) { return tc::install_fault_word_tu(word) == cudaSuccess ? 0 : 1; }
+
 }  // namespace wetts

@@ -148,4 +148,6 @@ int launch_fused_rb(int C, FusedRbArgs a, cudaStream_t s) {
   return launch_any<false>(C, ring, a, grid, smem, s);
 }
 
+int fused_rb_install_fault_word(unsigned int* word) { return tc::install_fault_word_tu(word) == cudaSuccess ? 0 : 1; }
+
 }  // namespace wetts

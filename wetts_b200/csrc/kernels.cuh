@@ -195,6 +195,13 @@ void launch_transpose_blc(const float* in, float* out, int B, int L, int C, cuda
 void launch_audio_to_int16(const float* audio, const long long* lengths, int B, long long L, int mode, float* peak,
                            short* out, cudaStream_t s);
 
+// soft watchdog of the mbarrier pipelines (tc_prims.cuh): every translation unit with waits installs the host-visible
+// fault word on the current device
+int tc_conv_install_fault_word(unsigned int* word);
+int tc16_conv_install_fault_word(unsigned int* word);
+int fused_rb_install_fault_word(unsigned int* word);
+int fused_mrf16_install_fault_word(unsigned int* word);
+
 unsigned long long kernel_launch_counter();
 void count_launch();
 

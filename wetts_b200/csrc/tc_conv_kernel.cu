@@ -603,4 +603,6 @@ void launch_conv1d_tc(const ConvArgs& a, cudaStream_t s) {
   count_launch();
 }
 
+int tc_conv_install_fault_word(unsigned int* word) { return tc::install_fault_word_tu(word) == cudaSuccess ? 0 : 1; }
+
 }  // namespace wetts

@@ -39,22 +39,36 @@ WETTS_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
 WETTS_DEVICE void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// Bounded spin: a pipeline bug must fail fast (trap -> launch failure) instead of hanging the GPU.
-// The loop lives inside ONE asm statement on purpose: a C++ loop around try_wait makes the compiler treat
-// everything after it as potentially divergent, which forces every later tcgen05.mma operand through R2UR
-// (measured: 240 -> 57 R2UR in the fused kernel, see DESIGN.md "issue path").
+// Watchdog.  A pipeline bug must fail fast instead of hanging the GPU: after 2^24 failed polls the wait records the
+// reason in a host-visible word (mapped pinned memory, one per process, installed per translation unit and device by
+// install_fault_word_tu(); it stays readable after the context is lost) and traps -> launch failure; the host reports
+// "pipeline watchdog fired" instead of an anonymous launch failure (engine.cu take_fault()).
+// A non-trapping variant (record the fault, fall through, let the kernel drain) was built and measured in SASS: it
+// costs the issue path its uniformity -- the wait loop then has an exit that is not guarded by the try_wait predicate,
+// ptxas treats everything after the wait as potentially divergent, every later tcgen05.mma is predicated and its
+// operands go through R2UR (fused_resblock2: 27 -> 449 R2UR, per-layer kernel: 16 -> 231).  The dead-end form below
+// keeps the control-flow shape of a plain bounded spin.  The loop lives inside ONE asm statement for the same reason
+// (a C++ loop around try_wait: 240 -> 57 R2UR in the fused kernel, DESIGN.md "issue path").
+__constant__ unsigned int* c_fault_word = nullptr;   // per translation unit and device
+static inline cudaError_t install_fault_word_tu(unsigned int* word) {   // call once per device from each .cu that waits
+  return cudaMemcpyToSymbol(c_fault_word, &word, sizeof(word));
+}
 WETTS_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
+  unsigned int* fw = c_fault_word;
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "{\n\t.reg .pred p, q;\n\t.reg .u32 n, f;\n\t"
       "mov.u32 n, 0;\n"
       "WAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "add.u32 n, n, 1;\n\t"
-      "setp.gt.u32 p, n, 0x1000000;\n\t"
-      "@p trap;\n\t"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
+      "setp.le.u32 q, n, 0x1000000;\n\t"
+      "@q bra WAIT_LOOP;\n\t"
+      "setp.ne.u64 q, %2, 0;\n\t"
+      "mov.u32 f, 1;\n\t"
+      "@q st.volatile.global.u32 [%2], f;\n\t"        // tell the host why
+      "trap;\n"
+      "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "l"(fw)
       : "memory");
 }
 WETTS_DEVICE void mbar_expect_tx(uint32_t bar, uint32_t bytes) {

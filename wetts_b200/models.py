@@ -309,6 +309,13 @@ class SynthesizerTrn:
     def launch_count(self):
         return self._engine.launch_count()
 
+    def check_faults(self, synchronize=True):
+        """Raises WettsError if a device-side pipeline wait timed out (soft watchdog, include/wetts_b200.h)."""
+        e = self._engine
+        e.ready()
+        check(e.lib.wetts_vits_check_fault(e.handle, _stream(e.device), int(bool(synchronize))))
+        return self
+
     def set_option(self, name, value):
         """Per-model engine option ("tensor_cores", "fused_resblock", "length_aware"); see include/wetts_b200.h."""
         e = self._engine
