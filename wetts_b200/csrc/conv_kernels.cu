@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv1d_kernel(const ConvArgs a) {
   const int co0 = warp_co * kTM;
   const int tl = warp_t * 32 * TN + lane;
   const int T = a.T;
+  if (a.la_len && (long long)t0 >= (a.la_len[b] + a.la_margin) * (long long)a.la_rate) return;   // length-aware: whole tile unused
   const long long len = a.lengths ? a.lengths[b] : (long long)T;
 
   float acc[kTM][TN];
@@ -348,9 +349,11 @@ __global__ void __launch_bounds__(kThreads) conv_post_kernel(const float* __rest
 // channel (its own quad plus the two neighbouring quads, which its neighbour threads also load: L1 hits), so
 // the kernel is a pure streaming read of the activation (HBM-bound) instead of one shared-memory load per FMA.
 __global__ void __launch_bounds__(kThreads) conv_post7_vec_kernel(const float* __restrict__ in, const float* __restrict__ w,
-                                                                 float* __restrict__ out, int C, int T, float slope) {
+                                                                 float* __restrict__ out, int C, int T, float slope,
+                                                                 const long long* __restrict__ la_len, int la_rate, int la_margin) {
   extern __shared__ __align__(16) float wsm[];   // [C][8] (tap 7 = 0)
   const int b = blockIdx.y, tid = threadIdx.x;
+  if (la_len && (long long)blockIdx.x * kThreads * 4 >= (la_len[b] + la_margin) * (long long)la_rate) return;   // length-aware
   for (int i = tid; i < C * 8; i += kThreads) wsm[i] = ((i & 7) < 7) ? w[(i >> 3) * 7 + (i & 7)] : 0.f;
   __syncthreads();
   const int q = blockIdx.x * kThreads + tid;   // quad index
@@ -458,10 +461,10 @@ void launch_conv_transpose1d(const ConvTArgs& a, cudaStream_t s) {
 }
 
 void launch_conv_post_tanh(const float* in, const float* w, float* out, int B, int C, int T, int K, float slope,
-                           cudaStream_t s) {
+                           cudaStream_t s, const long long* la_len, int la_rate, int la_margin) {
   if (K == 7 && (T & 3) == 0 && C <= 512 && (((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
     dim3 grid((T / 4 + kThreads - 1) / kThreads, B);
-    conv_post7_vec_kernel<<<grid, kThreads, (size_t)C * 8 * sizeof(float), s>>>(in, w, out, C, T, slope);
+    conv_post7_vec_kernel<<<grid, kThreads, (size_t)C * 8 * sizeof(float), s>>>(in, w, out, C, T, slope, la_len, la_rate, la_margin);
     count_launch();
     return;
   }

@@ -1138,6 +1138,11 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
     a.ep.cond = w.cvec;
     a.ep.cond_bs = c.upsample_initial_channel;
   }
+  // length-aware mode: frames beyond len + kLaMargin (> the generator's receptive field in frames) are not computed
+  constexpr int kLaMargin = 16;
+  const long long* la = (g_call.len_aware && y_lengths) ? (const long long*)y_lengths : nullptr;
+  auto set_la = [&](ConvArgs& ca, int rate) { ca.la_len = la; ca.la_rate = rate; ca.la_margin = kLaMargin; };
+  set_la(a, 1);
   int cur = 0;
   a.ep.out = w.x[cur];
   launch_conv1d(a, s);
@@ -1159,6 +1164,7 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
       ca.pre_act = 1; ca.pre_slope = 0.1f;
       ca.ep.mode = EPI_CONVT; ca.ep.out = w.xu; ca.ep.out_bs = (long long)up.Cout * len * up.u;
       ca.ep.up_u = up.u; ca.ep.up_pad = up.pad; ca.ep.out_T = (long long)len * up.u;
+      set_la(ca, len / T);
       if (up16) launch_conv1d_tc16(ca, s); else launch_conv1d_tc(ca, s);
     } else {
       launch_conv_transpose1d(ta, s);
@@ -1181,8 +1187,7 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
           fa.bias[j][cc] = cv.b;
         }
       }
-      if (g_call.len_aware && y_lengths)   // frames beyond len + 16 (> the generator's receptive field) are not computed
-        launch_mrf_item_map((const long long*)y_lengths, B, len, len / T, 16, w.item_map, &fa.item_map, &fa.n_items_dev, s);
+      if (la) launch_mrf_item_map(la, B, len, len / T, kLaMargin, w.item_map, &fa.item_map, &fa.n_items_dev, s);
       if (launch_fused_mrf16(ch, fa, s)) return fail("fused MRF (f16) launch failed");
       cur ^= 1;
       continue;
@@ -1210,11 +1215,13 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
         if (c.resblock_type == 1) {
           ConvArgs c1 = conv_args(rb.c1[n], curp, bs, len, B, len, rb.dil[n]);
           c1.pre_act = 1; c1.pre_slope = 0.1f; c1.ep.out = w.t;
+          set_la(c1, len / T);
           launch_conv1d(c1, s);
           ConvArgs c2 = conv_args(rb.c2[n], w.t, bs, len, B, len, 1);
           c2.pre_act = 1; c2.pre_slope = 0.1f; c2.ep.resid = curp;
           if (last) { c2.ep.mode = EPI_MRF; c2.ep.acc_mode = acc_mode; c2.ep.div = (float)nk; c2.ep.out = acc; }
           else { c2.ep.mode = EPI_RESID; c2.ep.out = w.r; }
+          set_la(c2, len / T);
           launch_conv1d(c2, s);
           curp = w.r;
         } else {
@@ -1227,6 +1234,7 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
             if (!dst) return fail("ResBlock2 with more than 2 dilations is not supported");
             c1.ep.mode = EPI_RESID; c1.ep.out = dst;
           }
+          set_la(c1, len / T);
           launch_conv1d(c1, s);
           curp = w.r;
         }
@@ -1234,7 +1242,7 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
     }
     cur ^= 1;
   }
-  launch_conv_post_tanh(w.x[cur], h->conv_post_w, audio, B, h->c_last, len, 7, 0.01f, s);
+  launch_conv_post_tanh(w.x[cur], h->conv_post_w, audio, B, h->c_last, len, 7, 0.01f, s, la, len / T, kLaMargin);
   CHECK_LAUNCH();
   return 0;
 }

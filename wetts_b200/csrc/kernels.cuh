@@ -67,6 +67,11 @@ struct ConvArgs {
   const long long* lengths = nullptr;  // int64[B] or nullptr
   int in_mask = 0;            // multiply the input by (t < lengths[b])
   int use_tc = 1;             // 0: force the fp32 SIMT kernel for this call (per-handle / process option)
+  // length-aware mode (optional): work whose first output row lies at or beyond (la_len[b] + la_margin) * la_rate is
+  // skipped (la_len in frames of z, la_rate = rows of THIS conv's time axis per frame); the skipped output rows are
+  // left unwritten
+  const long long* la_len = nullptr;
+  int la_rate = 1, la_margin = 0;
   ConvEpilogue ep;
 };
 void launch_conv1d(const ConvArgs& a, cudaStream_t s);
@@ -126,7 +131,7 @@ void launch_conv_transpose1d(const ConvTArgs& a, cudaStream_t s);
 
 // conv_post: lrelu(slope) -> Conv1d(C->1, k, no bias) -> tanh   (decoders.py:78-80)
 void launch_conv_post_tanh(const float* in, const float* w /*[C][K]*/, float* out, int B, int C, int T, int K,
-                           float slope, cudaStream_t s);
+                           float slope, cudaStream_t s, const long long* la_len = nullptr, int la_rate = 1, int la_margin = 0);
 
 // ---------------------------------------------------------------- weight preparation
 void launch_weight_norm_fold(const float* v, const float* g, float* out, int rows, int cols, cudaStream_t s);
