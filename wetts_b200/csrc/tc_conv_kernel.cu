@@ -248,11 +248,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
     const int rem = item - nt * items_per_nt;
     const int b = rem / n_groups;
     const int t_group0 = (rem - b * n_groups) * group_rows;
-    if (a.la_len) {   // length-aware mode: nothing of this group is needed (decision rebuilt from a vote: uniform)
-      const bool beyond = (long long)t_group0 >= (a.la_len[b] + a.la_margin) * (long long)a.la_rate;
-      if (uniform_bits(beyond ? 1u : 0u, 0, 1)) continue;
-    }
-    const int tiles = min(G, (T - t_group0 + MT - 1) / MT);
+    // length-aware mode: a group wholly beyond (len + margin) frames runs with zero tiles (no staging, no MMAs, empty
+    // epilogue; the per-item barriers still tick).  A select, not a branch (SASS-checked: a `continue` here, or votes
+    // on the tile count, cost the issue loop its uniform datapath: R2UR 19 -> 162).
+    int tiles = min(G, (T - t_group0 + MT - 1) / MT);
+    if (a.la_len) tiles = ((long long)t_group0 >= (a.la_len[b] + a.la_margin) * (long long)a.la_rate) ? 0 : tiles;
     const long long len = a.lengths ? a.lengths[b] : (long long)T;
     // per-item additive term of every output channel (bias + speaker conditioning), double buffered
     float* av = addv + (item_count & 1) * 256;
