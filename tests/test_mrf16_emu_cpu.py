@@ -67,3 +67,23 @@ def test_emulator_detects_broken_mrf16_kernels(tmp_path, name):
     args = ["1", "32", "2", "300", "2", "3", "6"] if name == "inner_conv_overwrites_x" else ["2", "32", "2", "300", "2", "3", "4"]
     r = subprocess.run([out] + args, capture_output=True, text=True, timeout=900)
     assert r.returncode != 0, "the emulator accepted a kernel with a known defect:\n" + r.stdout
+
+
+# ---- tensor-pipe attention kernel (attn_tc_kernel.cuh) in the same emulator
+@pytest.fixture(scope="module")
+def attn_emu_binary(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("emu_attn") / "attn_tc_emu")
+    subprocess.run([gxx, "-O2", "-std=c++20", "-pthread", "-x", "c++", "-I", EMU, "-I", os.path.join(ROOT, "wetts_b200", "csrc"),
+                    os.path.join(EMU, "attn_tc_emu.cpp"), "-o", out], check=True, capture_output=True, text=True)
+    return out
+
+
+# (B, T, lengths...): full tile, ragged lengths incl. a nearly empty utterance (invalid query rows), short texts
+@pytest.mark.parametrize("case", [(2, 128, 128, 80), (3, 100, 100, 37, 1), (1, 64, 64), (2, 7, 7, 3)])
+def test_attention_tc_kernel_in_emulator(attn_emu_binary, case):
+    """windowed relative-position attention (attentions.py:232-282) on the emulated tensor pipe vs an fp64 evaluation"""
+    r = subprocess.run([attn_emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -46,7 +46,7 @@ static int ensure_fault_word(int device) {
   unsigned int* dptr = nullptr;
   if (cudaHostGetDevicePointer((void**)&dptr, w, 0) != cudaSuccess) return 1;
   return tc_conv_install_fault_word(dptr) | tc16_conv_install_fault_word(dptr) | fused_rb_install_fault_word(dptr) |
-         fused_mrf16_install_fault_word(dptr);
+         fused_mrf16_install_fault_word(dptr) | attn_tc_install_fault_word(dptr);
 }
 // nonzero (and the word cleared) if a device-side pipeline wait timed out since the last check
 static unsigned int take_fault() {
@@ -853,7 +853,12 @@ int wetts_text_encoder_forward(wetts_vits_t h, const int64_t* ids, const int64_t
     ConvArgs a = conv_args(L.qkv, x, (long long)H * Tx, Tx, B, Tx);
     a.ep.out = w.qkv;
     launch_conv1d(a, s);
-    launch_rel_attention(w.qkv, L.rel_k, L.rel_v, len, w.att, B, H, Tx, c.n_heads, 4, s);
+    if (g_call.tc && rel_attention_tc_supported(H, Tx, c.n_heads, 4)) {
+      if (launch_rel_attention_tc(w.qkv, L.rel_k, L.rel_v, len, w.att, B, H, Tx, c.n_heads, 4, s))
+        return fail("tensor-pipe attention launch failed");
+    } else {
+      launch_rel_attention(w.qkv, L.rel_k, L.rel_v, len, w.att, B, H, Tx, c.n_heads, 4, s);
+    }
     a = conv_args(L.o, w.att, (long long)H * Tx, Tx, B, Tx);
     a.ep.out = w.y;
     launch_conv1d(a, s);

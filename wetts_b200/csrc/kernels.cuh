@@ -173,6 +173,11 @@ void launch_layernorm(const LnArgs& a, cudaStream_t s);
 // qkv [B][3C][T] (q rows 0..C-1, k rows C..2C-1, v rows 2C..3C-1), out [B][C][T]
 void launch_rel_attention(const float* qkv, const float* emb_k, const float* emb_v, const long long* lengths, float* out,
                           int B, int C, int T, int n_heads, int window, cudaStream_t s);
+// the same contraction on the tensor pipe (attn_tc.cu; 64 <= T <= 128, head dimension 96, window 4)
+bool rel_attention_tc_supported(int C, int T, int n_heads, int window);
+int launch_rel_attention_tc(const float* qkv, const float* emb_k, const float* emb_v, const long long* lengths, float* out,
+                            int B, int C, int T, int n_heads, int window, cudaStream_t s);
+int attn_tc_install_fault_word(unsigned int* word);
 
 // ---------------------------------------------------------------- stochastic duration predictor
 // h[b][c][t] = w[c]*z[b][src_ch][t] + bias[c] + cond[b][c][t]    (ConvFlow.pre + DDSConv `x + g`)
