@@ -326,6 +326,8 @@ def run_ours(args):
     _lib.check(lib.wetts_set_option(b"fused_resblock", int(args.fused_resblock)))
     if args.tensor_format:
         _lib.check(lib.wetts_set_option(b"tensor_format", int(args.tensor_format)))
+    if args.attention_tc >= 0:
+        _lib.check(lib.wetts_set_option(b"attention_tensor_cores", int(args.attention_tc)))
     hps = builtin_config(cfg_name)
     sd = synth.make_state_dict(hps.model, wl["n_vocab"], wl["n_spk"], seed=hps.train.seed)
     net = wetts_b200.build_model(hps, wl["n_vocab"], wl["n_spk"], sd, dev)
@@ -626,6 +628,7 @@ def main():
     ap.add_argument("--fused-resblock", type=int, default=1, help="0: one launch per generator conv (no fused MRF stage kernel)")
     ap.add_argument("--tensor-format", type=int, default=0, choices=[0, 16, 32],
                     help="operand format of the fused stage kernels: 16 = f16 split, 32 = 3xTF32, 0 = library default")
+    ap.add_argument("--attention-tc", type=int, default=-1, help="1/0: text-encoder attention on the tensor pipe (-1: library default)")
     ap.add_argument("--length-aware", type=int, default=0, help="1: skip generator tiles beyond each utterance's own length")
     args = ap.parse_args()
     if args.impl == "reference":

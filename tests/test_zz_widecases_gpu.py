@@ -112,3 +112,24 @@ def test_text_encoder_tcgen05_vs_simt_at_tx128():
     for i in range(3):
         assert rel_rms_err(out[0][i], ref[i]) < 2e-5      # fp32 SIMT route: summation-order noise only
         assert rel_rms_err(out[1][i], ref[i]) < 1e-4      # tensor-pipe route: the stated block tolerance
+
+
+@pytest.mark.parametrize("name", ["aishell3_long", "v3_tx128"])
+def test_text_encoder_with_tensor_core_attention(name):
+    """attention_tensor_cores = 1: QK^T and PV of the text encoder's attention run as f16-split tcgen05 MMAs
+    (attn_tc.cu, 64 <= Tx <= 128); the encoder outputs must stay inside the block tolerance against the fixture."""
+    import wetts_b200
+    hps, sd, g, t = load_case(name)
+    net = wetts_b200.build_model(hps, int(g["n_vocab"]), int(g["n_speakers"]), sd, "cuda")
+    h0, m0, l0, _ = net.enc_p(t["x"], t["x_lengths"])
+    n0 = net.launch_count()
+    net.set_option("attention_tensor_cores", 1)
+    h1, m1, l1, _ = net.enc_p(t["x"], t["x_lengths"])
+    torch.cuda.synchronize()
+    net.check_faults()
+    for nm, a, ref in (("h", h1, t["h"]), ("m", m1, t["m_p_tx"]), ("logs", l1, t["logs_p_tx"])):
+        e = rel_rms_err(a.cpu(), ref)
+        print(f"{name}: text encoder with tensor-pipe attention {nm} {e:.3e}")
+        assert e < BLOCK_TOL
+    assert not torch.equal(h0, h1), "the option must change the arithmetic route"
+    assert net.launch_count() > n0

@@ -26,8 +26,10 @@ static thread_local std::string g_err;
 struct CallOpts {
   bool tc = true, fused = true, len_aware = false;
   int fmt = 32;   // operand format of the fused stage kernels: 32 = 3xTF32 (kind::tf32), 16 = f16 split (kind::f16)
+  bool attn_tc = false;
 };
 static std::atomic<int> g_tensor_format{32};
+static std::atomic<int> g_attn_tc{0};   // text-encoder attention on the tensor pipe (attn_tc.cu) for 64 <= Tx <= 128
 
 // Host-visible fault word of the device-side soft watchdog (tc_prims.cuh mbar_wait): one mapped pinned word per
 // process, installed on every device a handle is created on.
@@ -143,7 +145,7 @@ struct wetts_vits_s {
   std::map<std::string, Raw> raw;
   std::vector<void*> owned;
   // per-handle options: -1 = follow the process-wide option (wetts_set_option)
-  int opt_tc = -1, opt_fused = -1, opt_len_aware = 0, opt_fmt = -1;
+  int opt_tc = -1, opt_fused = -1, opt_len_aware = 0, opt_fmt = -1, opt_attn_tc = -1;
   unsigned long long launches_at_create = 0;
   int U = 1;
 
@@ -464,6 +466,10 @@ int wetts_set_option(const char* name, int value) {
     g_tensor_format.store(value);
     return 0;
   }
+  if (!strcmp(name, "attention_tensor_cores")) {
+    g_attn_tc.store(value != 0);
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int wetts_get_option(const char* name, int* value) {
@@ -480,6 +486,10 @@ int wetts_get_option(const char* name, int* value) {
     *value = g_tensor_format.load();
     return 0;
   }
+  if (!strcmp(name, "attention_tensor_cores")) {
+    *value = g_attn_tc.load();
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int wetts_vits_set_option(wetts_vits_t h, const char* name, int value) {
@@ -490,7 +500,8 @@ int wetts_vits_set_option(wetts_vits_t h, const char* name, int value) {
   else if (!strcmp(name, "tensor_format")) {
     if (value != 16 && value != 32 && value >= 0) return fail("tensor_format must be 16, 32 or -1 (process default)");
     h->opt_fmt = value;
-  } else return fail("unknown option '%s'", name);
+  } else if (!strcmp(name, "attention_tensor_cores")) h->opt_attn_tc = value < 0 ? -1 : (value != 0);
+  else return fail("unknown option '%s'", name);
   return 0;
 }
 int wetts_vits_get_option(wetts_vits_t h, const char* name, int* value) {
@@ -499,6 +510,7 @@ int wetts_vits_get_option(wetts_vits_t h, const char* name, int* value) {
   else if (!strcmp(name, "fused_resblock")) *value = h->opt_fused >= 0 ? h->opt_fused : (fused_resblock_enabled() ? 1 : 0);
   else if (!strcmp(name, "length_aware")) *value = h->opt_len_aware;
   else if (!strcmp(name, "tensor_format")) *value = h->opt_fmt > 0 ? h->opt_fmt : g_tensor_format.load();
+  else if (!strcmp(name, "attention_tensor_cores")) *value = h->opt_attn_tc >= 0 ? h->opt_attn_tc : g_attn_tc.load();
   else return fail("unknown option '%s'", name);
   return 0;
 }
@@ -797,7 +809,8 @@ int wetts_vits_finalize(wetts_vits_t h) {
   g_call.tc = ((h)->opt_tc >= 0 ? (h)->opt_tc != 0 : tensor_cores_enabled());                 \
   g_call.fused = ((h)->opt_fused >= 0 ? (h)->opt_fused != 0 : fused_resblock_enabled());      \
   g_call.len_aware = (h)->opt_len_aware != 0;                                                 \
-  g_call.fmt = ((h)->opt_fmt > 0 ? (h)->opt_fmt : g_tensor_format.load());
+  g_call.fmt = ((h)->opt_fmt > 0 ? (h)->opt_fmt : g_tensor_format.load());                     \
+  g_call.attn_tc = ((h)->opt_attn_tc >= 0 ? (h)->opt_attn_tc != 0 : g_attn_tc.load() != 0);
 
 #define CHECK_LAUNCH()                                                                                   \
   do {                                                                                                   \
@@ -853,7 +866,7 @@ int wetts_text_encoder_forward(wetts_vits_t h, const int64_t* ids, const int64_t
     ConvArgs a = conv_args(L.qkv, x, (long long)H * Tx, Tx, B, Tx);
     a.ep.out = w.qkv;
     launch_conv1d(a, s);
-    if (g_call.tc && rel_attention_tc_supported(H, Tx, c.n_heads, 4)) {
+    if (g_call.tc && g_call.attn_tc && rel_attention_tc_supported(H, Tx, c.n_heads, 4)) {
       if (launch_rel_attention_tc(w.qkv, L.rel_k, L.rel_v, len, w.att, B, H, Tx, c.n_heads, 4, s))
         return fail("tensor-pipe attention launch failed");
     } else {
