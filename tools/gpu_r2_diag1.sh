@@ -27,3 +27,5 @@ WETTS_FUSED_RB_PROFILE=1 timeout 200 python bench.py --steps 1 --warmup 1 --no-c
 for ctas in 2; do
   WETTS_MRF16_CTAS=$ctas timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu --tensor-format 16 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('mrf16 ctas/sm(C=32)=$ctas ms/step', round(d['ms_per_step'],2), 'gen', round(d['roofline']['ms'],2))"
 done
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu --tensor-format 16 --attention-tc 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('fmt16 + tensor-pipe attention: ms/step', round(d['ms_per_step'],2), 'gen', round(d['roofline']['ms'],2))"
+timeout 200 python bench.py --steps 5 --warmup 3 --no-cpu --tensor-format 16 --attention-tc 1 --length-aware 1 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('fmt16 + attn + length-aware: ms/step', round(d['ms_per_step'],2), 'gen', round(d['roofline']['ms'],2))"
