@@ -68,6 +68,15 @@ typedef struct wetts_vits_config {
   int32_t upsample_rates[WETTS_MAX_UPSAMPLES];
   int32_t upsample_kernel_sizes[WETTS_MAX_UPSAMPLES];
   int32_t upsample_initial_channel;
+  /* SURVEY.md 8f rank 4 (the vits2_vocos_v1 recipe); all zero = the v1/v2/v3 recipes */
+  int32_t vocoder_type;        /* 0: HiFi-GAN Generator (decoders.py:15), 1: VocosGenerator (decoders.py:250) */
+  int32_t vocos_channels;      /* 512 */
+  int32_t vocos_h_channels;    /* 1536 */
+  int32_t vocos_out_channels;  /* 1026 = n_fft + 2 */
+  int32_t vocos_num_layers;    /* 8 */
+  int32_t vocos_n_fft;         /* 1024 (= win_length; center = True) */
+  int32_t vocos_hop_length;    /* 256 */
+  int32_t flow_type;           /* 0: ResidualCouplingLayer (flows.py:459), 1: VITS2 'pre_conv' transformer flow (flows.py:89) */
 } wetts_vits_config;
 
 const char* wetts_last_error(void);

@@ -35,6 +35,8 @@ CASES = [
     # the route bench.py measures: multilingual v3 at Tx = 128, ragged (every text-encoder / duration-predictor conv takes
     # the tcgen05 kernel at T >= 64); gating fixture for own-duration equality on that route
     ("v3_tx128", "multilingual_v3", 256, 2, [128, 97, 64], (0.667, 2.0, 0.8), 5684),
+    # the vits2_vocos_v1 recipe (Vocos iSTFT decoder + VITS2 'pre_conv' transformer flows, SDP)
+    ("vits2_vocos_short", "baker_vits2_vocos_v1", 64, 1, [9, 6], (0.667, 2.0, 0.8), 5685),
 ]
 
 # phoneme string of the wetts.cli example utterance and the synthetic phones.txt rule

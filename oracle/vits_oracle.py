@@ -241,6 +241,38 @@ def dense_path(idx, Tx):
     return (idx[:, :, None] == torch.arange(Tx)[None, None, :]).to(torch.float32)[:, None]
 
 
+# --------------------------------------------------------------------------- VITS2 transformer flow pieces
+def plain_encoder(w, prefix, x, mask, n_layers, n_heads, ks):
+    """attentions.Encoder.forward (attentions.py:70-87) with window_size=None: plain multi-head attention
+    (attentions.py:232-246,262-272, no relative-position terms), FFN k=ks (:403-411), channel LayerNorms.
+    x [B,C,T], mask [B,T]."""
+    B, C, T = x.shape
+    dk = C // n_heads
+    m3 = mask[:, None, :]
+    pl, pr = (ks - 1) // 2, ks // 2
+    x = x * m3
+    pair = mask[:, None, :, None] * mask[:, None, None, :]
+    for i in range(n_layers):
+        a = f"{prefix}.attn_layers.{i}"
+        q = F.conv1d(x, w[a + ".conv_q.weight"], w[a + ".conv_q.bias"])
+        k = F.conv1d(x, w[a + ".conv_k.weight"], w[a + ".conv_k.bias"])
+        v = F.conv1d(x, w[a + ".conv_v.weight"], w[a + ".conv_v.bias"])
+        qh = q.view(B, n_heads, dk, T).transpose(2, 3) / math.sqrt(dk)
+        kh = k.view(B, n_heads, dk, T).transpose(2, 3)
+        vh = v.view(B, n_heads, dk, T).transpose(2, 3)
+        scores = (qh @ kh.transpose(-2, -1)).masked_fill(pair == 0, -1e4)
+        y = (torch.softmax(scores, dim=-1) @ vh).transpose(2, 3).reshape(B, C, T)
+        y = F.conv1d(y, w[a + ".conv_o.weight"], w[a + ".conv_o.bias"])
+        n1 = f"{prefix}.norm_layers_1.{i}"
+        x = channel_layer_norm(x + y, w[n1 + ".gamma"], w[n1 + ".beta"])
+        f = f"{prefix}.ffn_layers.{i}"
+        y = torch.relu(F.conv1d(F.pad(x * m3, (pl, pr)), w[f + ".conv_1.weight"], w[f + ".conv_1.bias"]))
+        y = F.conv1d(F.pad(y * m3, (pl, pr)), w[f + ".conv_2.weight"], w[f + ".conv_2.bias"]) * m3
+        n2 = f"{prefix}.norm_layers_2.{i}"
+        x = channel_layer_norm(x + y, w[n2 + ".gamma"], w[n2 + ".beta"])
+    return x * m3
+
+
 # --------------------------------------------------------------------------- flow
 def wn(w, prefix, x, m3, g, H, n_layers=4):
     """modules.py:60-87"""
@@ -265,11 +297,15 @@ def flow_reverse(w, cfg, z, y_m3, g):
     """flows.py:442-449 reversed list + flows.py:494-513 (mean_only, reverse)."""
     H = cfg["hidden_channels"]
     half = cfg["inter_channels"] // 2
+    tflow = cfg.get("use_transformer_flows", False)      # 'pre_conv' type: flows.py:89-176
     for f in (6, 4, 2, 0):
         z = torch.flip(z, [1])
         p = f"flow.flows.{f}"
         x0, x1 = z[:, :half], z[:, half:]
-        h = F.conv1d(x0, w[p + ".pre.weight"], w[p + ".pre.bias"]) * y_m3
+        xin = x0
+        if tflow:   # flows.py:148-151: x0_ = pre_transformer(x0 * mask, mask) + x0 ; pre() sees x0_
+            xin = plain_encoder(w, p + ".pre_transformer", x0 * y_m3, y_m3[:, 0], 2, 2, 3) + x0
+        h = F.conv1d(xin, w[p + ".pre.weight"], w[p + ".pre.bias"]) * y_m3
         h = wn(w, p + ".enc", h, y_m3, g, H)
         m = F.conv1d(h, w[p + ".post.weight"], w[p + ".post.bias"]) * y_m3
         x1 = (x1 - m) * y_m3
@@ -277,9 +313,60 @@ def flow_reverse(w, cfg, z, y_m3, g):
     return z
 
 
+# --------------------------------------------------------------------------- Vocos generator
+def istft_hann(re, im, n_fft, hop):
+    """torch.istft(center=True, periodic hann window, normalized=False, onesided) restated: per-frame inverse real DFT,
+    windowing, overlap-add, division by the overlap-added squared window, n_fft/2 trimmed at both ends
+    (what torchaudio's InverseSpectrogram, decoders.py:277-282,303-306, evaluates).  re, im [B, n_fft/2+1, F]."""
+    B, _, Fr = re.shape
+    n = torch.arange(n_fft, dtype=torch.float64)
+    k = torch.arange(n_fft // 2 + 1, dtype=torch.float64)
+    ang = 2 * math.pi * k[:, None] * n[None, :] / n_fft                       # [K, N]
+    ck = torch.full((n_fft // 2 + 1,), 2.0, dtype=torch.float64)
+    ck[0] = ck[-1] = 1.0
+    cosb, sinb = (ck[:, None] * torch.cos(ang)) / n_fft, (ck[:, None] * torch.sin(ang)) / n_fft
+    sinb[0] = sinb[-1] = 0.0                                                   # imaginary parts of DC / Nyquist are ignored
+    win = torch.hann_window(n_fft, periodic=True, dtype=torch.float64)
+    frames = (re.double().transpose(1, 2) @ cosb - im.double().transpose(1, 2) @ sinb) * win    # [B, F, N]
+    L = hop * (Fr - 1) + n_fft
+    out = torch.zeros(B, L, dtype=torch.float64)
+    env = torch.zeros(L, dtype=torch.float64)
+    for f in range(Fr):
+        out[:, f * hop: f * hop + n_fft] += frames[:, f]
+        env[f * hop: f * hop + n_fft] += win * win
+    half = n_fft // 2
+    return (out[:, half: L - half] / env[half: L - half]).float()
+
+
+def vocos_generator(w, cfg, z, g):
+    """VocosGenerator.forward (decoders.py:287-307) with ConvNeXtLayer.forward (:239-247)."""
+    x = F.pad(z, (1, 0), mode="reflect")
+    x = F.conv1d(x, w["dec.in_conv.weight"], w["dec.in_conv.bias"])
+    if g is not None:
+        x = x + F.conv1d(g, w["dec.cond.weight"], w["dec.cond.bias"])
+    x = channel_layer_norm(x, w["dec.norm_pre.gamma"], w["dec.norm_pre.beta"])
+    C = x.shape[1]
+    for i in range(cfg.get("vocos_num_layers", 8)):
+        p = f"dec.layers.{i}"
+        r = x
+        x = F.conv1d(x, w[p + ".dw_conv.weight"], w[p + ".dw_conv.bias"], padding=1, groups=C)
+        x = channel_layer_norm(x, w[p + ".norm.gamma"], w[p + ".norm.beta"])
+        x = F.gelu(F.conv1d(x, w[p + ".pw_conv1.weight"], w[p + ".pw_conv1.bias"]))
+        x = F.conv1d(x, w[p + ".pw_conv2.weight"], w[p + ".pw_conv2.bias"])
+        x = r + w[p + ".scale"] * x
+    x = channel_layer_norm(x, w["dec.norm_post.gamma"], w["dec.norm_post.beta"])
+    x = F.conv1d(x, w["dec.out_conv.weight"], w["dec.out_conv.bias"])
+    mag, phase = x.chunk(2, dim=1)
+    mag = mag.exp().clamp_max(1e2)
+    ic = cfg.get("vocos_istft_config", {"n_fft": 1024, "hop_length": 256})
+    return istft_hann(mag * phase.cos(), mag * phase.sin(), ic["n_fft"], ic["hop_length"])[:, None, :]
+
+
 # --------------------------------------------------------------------------- generator
 def generator(w, cfg, z, g):
     """decoders.py:63-82 + ResBlock1 :157-170 / ResBlock2 :205-214."""
+    if cfg.get("vocoder_type", "hifigan") == "vocos":
+        return vocos_generator(w, cfg, z, g)
     x = F.conv1d(z, w["dec.conv_pre.weight"], w["dec.conv_pre.bias"], padding=3)
     if g is not None:
         x = x + F.conv1d(g, w["dec.cond.weight"], w["dec.cond.bias"])

@@ -14,6 +14,8 @@ CASES = ["v3_ragged", "v3_single", "v1_ragged", "v2_short"]
 # text-encoder / duration-predictor conv takes the tcgen05 kernel): pinned on the CPU with the other fixtures; on the
 # GPU they gate in tests/test_zz_widecases_gpu.py.
 WIDE_CASES = ["aishell3_long", "baker_v1_cli", "v3_tx128"]
+# the vits2_vocos_v1 recipe (Vocos iSTFT decoder, VITS2 'pre_conv' transformer flows, SDP)
+VITS2_CASES = ["vits2_vocos_short"]
 
 
 def load_case(name):

@@ -62,9 +62,22 @@ def test_fails_loudly_without_gpu():
 def test_unsupported_variants_raise():
     hps = builtin_config("multilingual_v3")
     with pytest.raises(NotImplementedError):
-        wetts_b200.SynthesizerTrn(10, 513, 32, n_speakers=1, vocoder_type="vocos", **hps.model)
-    with pytest.raises(NotImplementedError):
-        wetts_b200.SynthesizerTrn(10, 513, 32, n_speakers=1, use_transformer_flows=True, **hps.model)
+        wetts_b200.SynthesizerTrn(10, 513, 32, n_speakers=1, vocoder_type="bigvgan", **hps.model)
+    with pytest.raises(NotImplementedError):    # only the 'pre_conv' transformer flow (vits2_vocos_v1 recipe) is built
+        wetts_b200.SynthesizerTrn(10, 513, 32, n_speakers=1, use_transformer_flows=True, transformer_flow_type="fft", **hps.model)
+
+
+def test_vits2_vocos_recipe_constructs_and_maps_its_config():
+    """the reference's vits2_vocos_v1 recipe file is accepted unchanged"""
+    hps = builtin_config("baker_vits2_vocos_v1")
+    net = wetts_b200.SynthesizerTrn(64, 513, 32, n_speakers=1, **hps.model)
+    c = net._engine.cfg
+    assert (c.vocoder_type, c.flow_type) == (1, 1)
+    assert (c.vocos_channels, c.vocos_h_channels, c.vocos_out_channels, c.vocos_num_layers) == (512, 1536, 1026, 8)
+    assert (c.vocos_n_fft, c.vocos_hop_length) == (1024, 256) and net._engine.upsample == 256
+    sd = synth.make_state_dict(hps.model, 64, 1, seed=1234)
+    assert "dec.layers.7.scale" in sd and "flow.flows.6.pre_transformer.attn_layers.1.conv_q.weight" in sd
+    assert "dec.conv_pre.weight" not in sd
 
 
 def test_reference_loads_synthetic_checkpoint():

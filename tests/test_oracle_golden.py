@@ -4,12 +4,12 @@ import pytest
 import torch
 
 from oracle import vits_oracle as O
-from tests.golden_util import CASES, WIDE_CASES, load_case, rel_rms_err
+from tests.golden_util import CASES, VITS2_CASES, WIDE_CASES, load_case, rel_rms_err
 
 TOL = 2e-5  # relative to rms; both sides are fp32 CPU, differences are summation order only
 
 
-@pytest.mark.parametrize("name", CASES + WIDE_CASES)
+@pytest.mark.parametrize("name", CASES + WIDE_CASES + VITS2_CASES)
 def test_oracle_matches_reference_fixture(name):
     hps, sd, g, t = load_case(name)
     ns, ls, nsw = [float(v) for v in g["scales"]]

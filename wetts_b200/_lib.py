@@ -22,6 +22,9 @@ class VitsConfig(C.Structure):
         ("upsample_rates", C.c_int32 * MAX_UPSAMPLES),
         ("upsample_kernel_sizes", C.c_int32 * MAX_UPSAMPLES),
         ("upsample_initial_channel", C.c_int32),
+        ("vocoder_type", C.c_int32), ("vocos_channels", C.c_int32), ("vocos_h_channels", C.c_int32),
+        ("vocos_out_channels", C.c_int32), ("vocos_num_layers", C.c_int32), ("vocos_n_fft", C.c_int32),
+        ("vocos_hop_length", C.c_int32), ("flow_type", C.c_int32),
     ]
 
 

@@ -171,10 +171,24 @@ struct wetts_vits_s {
   } cf[3];  // flows 7, 5, 3 in application order
   float *ea_m = nullptr, *ea_logs = nullptr;
   // flow
+  struct PlainEncLayer {   // attentions.Encoder layer with window_size=None (VITS2 pre_transformer)
+    Conv qkv, o, ffn1, ffn2;
+    Ln ln1, ln2;
+  };
   struct Coupling {
     Conv pre, post, cond, in[4], rs[4];
     bool flipped = false;
+    PlainEncLayer tf[2];   // flow_type 1 only
   } flow[4];  // application order: reference layers 6, 4, 2, 0
+  // Vocos generator (vocoder_type 1)
+  struct ConvNext {
+    float *dww = nullptr, *dwb = nullptr;
+    Ln norm;
+    Conv pw1, pw2;   // pw2 carries the layer scale
+  };
+  Conv voc_in, voc_cond, voc_out, voc_idft;
+  Ln voc_norm_pre, voc_norm_post;
+  std::vector<ConvNext> voc_layers;
   // generator
   Conv conv_pre, dec_cond;
   std::vector<ConvT> ups;
@@ -297,7 +311,7 @@ struct wetts_vits_s {
     l->g = g->d;
     l->b = b->d;
     l->C = (int)g->numel();
-    if (l->C > 256) return fail("LayerNorm over %d channels not supported (max 256)", l->C);
+    if (l->C > 512) return fail("LayerNorm over %d channels not supported (max 512)", l->C);
     return 0;
   }
   int make_dds(const std::string& prefix, Dds* d) {
@@ -412,19 +426,32 @@ int wetts_vits_create(const wetts_vits_config* cfg, int device, wetts_vits_t* ou
   if (c.hidden_channels % c.n_heads) return fail("hidden_channels %% n_heads != 0");
   if (c.hidden_channels / c.n_heads > 96) return fail("head dim %d > 96 not supported", c.hidden_channels / c.n_heads);
   if (c.hidden_channels > 256 || c.inter_channels % 2) return fail("unsupported channel configuration");
-  if (c.n_upsamples < 1 || c.n_upsamples > WETTS_MAX_UPSAMPLES) return fail("bad n_upsamples");
-  if (c.n_resblock_kernels < 1 || c.n_resblock_kernels > WETTS_MAX_RESBLOCK_KERNELS) return fail("bad n_resblock_kernels");
-  if (c.resblock_type != 1 && c.resblock_type != 2) return fail("resblock_type must be 1 or 2");
-  int U = 1;
-  for (int i = 0; i < c.n_upsamples; ++i) {
-    const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
-    if (u < 1 || 32 % u) return fail("upsample rate %d must divide 32", u);
-    if (k % u || (k - u) % 2) return fail("upsample kernel %d incompatible with rate %d", k, u);
-    U *= u;
+  if (c.vocoder_type != 0 && c.vocoder_type != 1) return fail("vocoder_type must be 0 (HiFi-GAN) or 1 (Vocos)");
+  if (c.flow_type != 0 && c.flow_type != 1) return fail("flow_type must be 0 or 1 ('pre_conv')");
+  if (c.vocoder_type == 1) {
+    if (c.vocos_channels < 16 || c.vocos_channels > 512) return fail("vocos_channels must be in [16, 512]");
+    if (c.vocos_n_fft < 16 || (c.vocos_n_fft & (c.vocos_n_fft - 1)) || c.vocos_out_channels != c.vocos_n_fft + 2)
+      return fail("Vocos: n_fft must be a power of two and out_channels = n_fft + 2");
+    if (c.vocos_hop_length < 1 || c.vocos_n_fft % c.vocos_hop_length) return fail("Vocos: hop_length must divide n_fft");
+    if (c.vocos_num_layers < 1 || c.vocos_h_channels < 16) return fail("bad Vocos layer configuration");
   }
-  for (int j = 0; j < c.n_resblock_kernels; ++j) {
-    if (c.resblock_kernel_sizes[j] % 2 == 0) return fail("resblock kernel sizes must be odd");
-    if (c.resblock_n_dilations[j] < 1 || c.resblock_n_dilations[j] > WETTS_MAX_DILATIONS) return fail("bad dilation count");
+  int U = 1;
+  if (c.vocoder_type == 1) {
+    U = c.vocos_hop_length;
+  } else {
+    if (c.n_upsamples < 1 || c.n_upsamples > WETTS_MAX_UPSAMPLES) return fail("bad n_upsamples");
+    if (c.n_resblock_kernels < 1 || c.n_resblock_kernels > WETTS_MAX_RESBLOCK_KERNELS) return fail("bad n_resblock_kernels");
+    if (c.resblock_type != 1 && c.resblock_type != 2) return fail("resblock_type must be 1 or 2");
+    for (int i = 0; i < c.n_upsamples; ++i) {
+      const int u = c.upsample_rates[i], k = c.upsample_kernel_sizes[i];
+      if (u < 1 || 32 % u) return fail("upsample rate %d must divide 32", u);
+      if (k % u || (k - u) % 2) return fail("upsample kernel %d incompatible with rate %d", k, u);
+      U *= u;
+    }
+    for (int j = 0; j < c.n_resblock_kernels; ++j) {
+      if (c.resblock_kernel_sizes[j] % 2 == 0) return fail("resblock kernel sizes must be odd");
+      if (c.resblock_n_dilations[j] < 1 || c.resblock_n_dilations[j] > WETTS_MAX_DILATIONS) return fail("bad dilation count");
+    }
   }
   if (c.kernel_size % 2 == 0) return fail("FFN kernel_size must be odd");
   wetts_vits_s* h = new wetts_vits_s();
@@ -650,6 +677,38 @@ int wetts_vits_finalize(wetts_vits_t h) {
         ci.resize(half);
         for (int q = 0; q < half; ++q) ci[q] = half - 1 - q;
       }
+      if (c.flow_type == 1) {
+        // VITS2 'pre_conv' coupling layer: x0 is materialised in the layer's own channel order (gather kernel), so the
+        // pre_transformer and `pre` take it unpermuted
+        ci.clear();
+        for (int i = 0; i < 2; ++i) {
+          auto& L = F.tf[i];
+          const std::string a = p + ".pre_transformer.attn_layers." + std::to_string(i);
+          Raw wq, wk, wv;
+          if (h->folded_weight(a + ".conv_q", &wq) || h->folded_weight(a + ".conv_k", &wk) || h->folded_weight(a + ".conv_v", &wv))
+            return 1;
+          const Raw *bq, *bk, *bv;
+          if (h->need(a + ".conv_q.bias", &bq) || h->need(a + ".conv_k.bias", &bk) || h->need(a + ".conv_v.bias", &bv)) return 1;
+          Raw cat;
+          cat.dims = {3 * half, half, 1};
+          float* catb;
+          if (h->dalloc(&cat.d, (size_t)3 * half * half) || h->dalloc(&catb, (size_t)3 * half)) return 1;
+          const Raw* ws[3] = {&wq, &wk, &wv};
+          const Raw* bs[3] = {bq, bk, bv};
+          for (int q = 0; q < 3; ++q) {
+            if ((int)ws[q]->numel() != half * half) return fail("%s: unexpected q/k/v weight size", a.c_str());
+            CUDA_OK(cudaMemcpy(cat.d + (size_t)q * half * half, ws[q]->d, sizeof(float) * half * half, cudaMemcpyDeviceToDevice));
+            CUDA_OK(cudaMemcpy(catb + (size_t)q * half, bs[q]->d, sizeof(float) * half, cudaMemcpyDeviceToDevice));
+          }
+          if (h->pack_conv_from(cat, catb, {}, {}, &L.qkv)) return 1;
+          if (h->make_conv(a + ".conv_o", &L.o)) return 1;
+          if (h->make_ln(p + ".pre_transformer.norm_layers_1." + std::to_string(i), &L.ln1)) return 1;
+          if (h->make_ln(p + ".pre_transformer.norm_layers_2." + std::to_string(i), &L.ln2)) return 1;
+          if (h->make_conv(p + ".pre_transformer.ffn_layers." + std::to_string(i) + ".conv_1", &L.ffn1)) return 1;
+          if (h->make_conv(p + ".pre_transformer.ffn_layers." + std::to_string(i) + ".conv_2", &L.ffn2)) return 1;
+          if (L.ffn1.K != 3 || L.ffn2.K != 3) return fail("%s: FFN kernel size must be 3", p.c_str());
+        }
+      }
       if (h->make_conv(p + ".pre", &F.pre, true, {}, ci)) return 1;
       if (h->make_conv(p + ".post", &F.post)) return 1;
       if (F.post.Cout != half) return fail("%s.post: only mean_only couplings are supported", p.c_str());
@@ -661,6 +720,46 @@ int wetts_vits_finalize(wetts_vits_t h) {
       }
     }
   }
+  // ---- Vocos generator (decoders.py:250-307)
+  if (c.vocoder_type == 1) {
+    const int vc = c.vocos_channels;
+    if (h->make_conv("dec.in_conv", &h->voc_in)) return 1;
+    if (gin && h->make_conv("dec.cond", &h->voc_cond)) return 1;
+    if (h->make_ln("dec.norm_pre", &h->voc_norm_pre) || h->make_ln("dec.norm_post", &h->voc_norm_post)) return 1;
+    h->voc_layers.resize(c.vocos_num_layers);
+    for (int i = 0; i < c.vocos_num_layers; ++i) {
+      auto& L = h->voc_layers[i];
+      const std::string p = "dec.layers." + std::to_string(i);
+      const Raw *w, *b, *sc;
+      if (h->need(p + ".dw_conv.weight", &w) || h->need(p + ".dw_conv.bias", &b)) return 1;
+      if (w->dims.size() != 3 || w->dims[0] != vc || w->dims[1] != 1 || w->dims[2] != 3)
+        return fail("%s.dw_conv: expected a depthwise kernel [%d,1,3]", p.c_str(), vc);
+      L.dww = w->d;
+      L.dwb = b->d;
+      if (h->make_ln(p + ".norm", &L.norm) || h->make_conv(p + ".pw_conv1", &L.pw1)) return 1;
+      // x = res + scale * pw_conv2(.): the layer scale is folded into pw_conv2's rows
+      Raw w2;
+      const Raw* b2;
+      if (h->folded_weight(p + ".pw_conv2", &w2) || h->need(p + ".pw_conv2.bias", &b2) || h->need(p + ".scale", &sc)) return 1;
+      if ((int)sc->numel() != vc || (int)w2.dims[0] != vc) return fail("%s.scale: unexpected shape", p.c_str());
+      Raw ws;
+      ws.dims = w2.dims;
+      float* bsc;
+      if (h->dalloc(&ws.d, w2.numel()) || h->dalloc(&bsc, (size_t)vc)) return 1;
+      launch_scale_rows(w2.d, b2->d, sc->d, ws.d, bsc, vc, (int)(w2.numel() / vc), 0);
+      if (h->pack_conv_from(ws, bsc, {}, {}, &L.pw2)) return 1;
+    }
+    if (h->make_conv("dec.out_conv", &h->voc_out)) return 1;
+    if (h->voc_out.Cout != c.vocos_out_channels) return fail("dec.out_conv: shape does not match the config");
+    {
+      Raw wi;   // inverse real DFT x periodic hann window as a constant 1x1 conv: [n_fft][n_fft + 2][1]
+      wi.dims = {(int64_t)c.vocos_n_fft, (int64_t)c.vocos_n_fft + 2, 1};
+      if (h->dalloc(&wi.d, wi.numel())) return 1;
+      launch_idft_weight(wi.d, c.vocos_n_fft, 0);
+      if (h->pack_conv_from(wi, nullptr, {}, {}, &h->voc_idft)) return 1;
+    }
+    h->c_last = vc;
+  } else
   // ---- generator
   {
     if (h->make_conv("dec.conv_pre", &h->conv_pre)) return 1;
@@ -1041,6 +1140,7 @@ int wetts_expand_prior(wetts_vits_t h, const float* m, const float* logs, const 
 // ------------------------------------------------------------------ flow
 struct FlowWs {
   float *gc, *hb, *acts, *skip;
+  float *x0, *xt, *qkv, *att, *y, *f;   // VITS2 'pre_conv' flows: x0 in layer order, encoder state and scratch (half channels)
 };
 static size_t flow_layout(const wetts_vits_config& c, int B, int Ty, Arena& A, FlowWs* w) {
   const size_t H = c.hidden_channels, n = (size_t)B * Ty;
@@ -1048,6 +1148,16 @@ static size_t flow_layout(const wetts_vits_config& c, int B, int Ty, Arena& A, F
   w->hb = A.take<float>(H * n);
   w->acts = A.take<float>(H * n);
   w->skip = A.take<float>(H * n);
+  w->x0 = w->xt = w->qkv = w->att = w->y = w->f = nullptr;
+  if (c.flow_type == 1) {
+    const size_t half = c.inter_channels / 2;
+    w->x0 = A.take<float>(half * n);
+    w->xt = A.take<float>(half * n);
+    w->qkv = A.take<float>(3 * half * n);
+    w->att = A.take<float>(half * n);
+    w->y = A.take<float>(half * n);
+    w->f = A.take<float>(half * n);
+  }
   return A.off;
 }
 size_t wetts_flow_workspace_bytes(wetts_vits_t h, int B, int Ty) {
@@ -1071,8 +1181,41 @@ int wetts_flow_reverse(wetts_vits_t h, float* z, const int64_t* y_lengths, const
   for (int j = 0; j < 4; ++j) {
     auto& F = h->flow[j];
     if (has_g) cond_vector(F.cond, g, B, w.gc, s);
-    // h = pre(x0) * mask
-    ConvArgs a = conv_args(F.pre, z + (F.flipped ? (long long)half * Ty : 0), (long long)Cc * Ty, Ty, B, Ty);
+    ConvArgs a;
+    if (c.flow_type == 1) {
+      // flows.py:146-151: x0_ = pre_transformer(x0 * mask, mask) + x0 ; h = pre(x0_) * mask.  x0 = the layer's first half
+      // in ITS channel order (after the Flips applied so far: the reversed second half of z when F.flipped)
+      if (Ty > 3000) return fail("Ty=%d exceeds the attention kernel limit (3000) of the transformer flow", Ty);
+      launch_gather_channels(z, (long long)Cc * Ty, F.flipped ? Cc - 1 : 0, F.flipped ? -1 : 1, len, w.x0, w.xt, B, half, Ty, s);
+      for (int i = 0; i < 2; ++i) {
+        auto& L = F.tf[i];
+        ConvArgs q = conv_args(L.qkv, w.xt, (long long)half * Ty, Ty, B, Ty);
+        q.ep.out = w.qkv;
+        launch_conv1d(q, s);
+        launch_rel_attention(w.qkv, nullptr, nullptr, len, w.att, B, half, Ty, 2, 0, s);
+        q = conv_args(L.o, w.att, (long long)half * Ty, Ty, B, Ty);
+        q.ep.out = w.y;
+        launch_conv1d(q, s);
+        LnArgs l;
+        l.a = w.xt; l.b = w.y; l.gamma = L.ln1.g; l.beta = L.ln1.b; l.out = w.xt; l.B = B; l.C = half; l.T = Ty;
+        launch_layernorm(l, s);
+        q = conv_args(L.ffn1, w.xt, (long long)half * Ty, Ty, B, Ty);
+        q.lengths = len; q.in_mask = 1; q.ep.act = 1; q.ep.out = w.f;
+        launch_conv1d(q, s);
+        q = conv_args(L.ffn2, w.f, (long long)half * Ty, Ty, B, Ty);
+        q.lengths = len; q.in_mask = 1; q.ep.out_mask = 1; q.ep.out = w.y;
+        launch_conv1d(q, s);
+        LnArgs l2;
+        l2.a = w.xt; l2.b = w.y; l2.gamma = L.ln2.g; l2.beta = L.ln2.b; l2.out = w.xt; l2.B = B; l2.C = half; l2.T = Ty;
+        l2.lengths = len;
+        if (i == 1) { l2.res = w.x0; l2.out_mask = 1; }   // (LN + x0) * mask: equals pre()'s masked input on every valid frame
+        launch_layernorm(l2, s);
+      }
+      a = conv_args(F.pre, w.xt, (long long)half * Ty, Ty, B, Ty);
+    } else {
+      // h = pre(x0) * mask
+      a = conv_args(F.pre, z + (F.flipped ? (long long)half * Ty : 0), (long long)Cc * Ty, Ty, B, Ty);
+    }
     a.lengths = len; a.ep.out_mask = 1; a.ep.out = w.hb;
     launch_conv1d(a, s);
     for (int i = 0; i < 4; ++i) {
@@ -1103,8 +1246,75 @@ struct GenWs {
   float *cvec, *x[2], *xu, *r, *t;
   void* item_map;   // length-aware mode: work-item list of the fused stage being launched
 };
+struct VocosWs {
+  float *cvec, *zp, *x, *y, *hid, *spec, *frames;
+};
+static size_t vocos_layout(const wetts_vits_config& c, int B, int T, Arena& A, VocosWs* w) {
+  const size_t n = (size_t)B * (T + 1);
+  w->cvec = A.take<float>((size_t)B * c.vocos_channels);
+  w->zp = A.take<float>((size_t)c.inter_channels * n);
+  w->x = A.take<float>((size_t)c.vocos_channels * n);
+  w->y = A.take<float>((size_t)c.vocos_channels * n);
+  w->hid = A.take<float>((size_t)c.vocos_h_channels * n);
+  w->spec = A.take<float>((size_t)c.vocos_out_channels * n);
+  w->frames = A.take<float>((size_t)c.vocos_n_fft * n);
+  return A.off;
+}
+// VocosGenerator.forward (decoders.py:287-307): reflection pad, in_conv + cond, LayerNorm, ConvNeXt layers (:239-247),
+// LayerNorm, out_conv, exp / cos / sin, inverse STFT (inverse real DFT as a constant 1x1 conv on the tensor pipe,
+// overlap-add with the squared-window envelope)
+static int vocos_forward(wetts_vits_t h, const float* z, int64_t z_bs, int64_t z_cs, const int64_t* y_lengths, const float* g,
+                         int B, int T, float* audio, void* workspace, size_t workspace_bytes, cudaStream_t s) {
+  const wetts_vits_config& c = h->cfg;
+  Arena A(workspace, workspace_bytes);
+  VocosWs w;
+  vocos_layout(c, B, T, A, &w);
+  if (!workspace || !A.ok()) return fail("generator workspace too small: need %zu bytes", A.off);
+  const int F = T + 1, vc = c.vocos_channels;
+  launch_reflect_pad_left(z, (long long)z_bs, (int)z_cs, (const long long*)y_lengths, w.zp, B, c.inter_channels, T, s);
+  ConvArgs a = conv_args(h->voc_in, w.zp, (long long)c.inter_channels * F, F, B, F);
+  if (g && c.gin_channels > 0) {
+    cond_vector(h->voc_cond, g, B, w.cvec, s);
+    a.ep.cond = w.cvec;
+    a.ep.cond_bs = vc;
+  }
+  a.ep.out = w.x;
+  launch_conv1d(a, s);
+  LnArgs l;
+  l.a = w.x; l.gamma = h->voc_norm_pre.g; l.beta = h->voc_norm_pre.b; l.out = w.x; l.B = B; l.C = vc; l.T = F;
+  launch_layernorm(l, s);
+  for (auto& L : h->voc_layers) {
+    LnArgs d;   // LayerNorm(dw_conv(x)): depthwise k3 front-end of the norm kernel
+    d.a = w.x; d.dww = L.dww; d.dwb = L.dwb; d.dil = 1; d.gamma = L.norm.g; d.beta = L.norm.b; d.out = w.y;
+    d.B = B; d.C = vc; d.T = F;
+    launch_layernorm(d, s);
+    a = conv_args(L.pw1, w.y, (long long)vc * F, F, B, F);
+    a.ep.act = 2; a.ep.out = w.hid;
+    launch_conv1d(a, s);
+    a = conv_args(L.pw2, w.hid, (long long)c.vocos_h_channels * F, F, B, F);
+    a.ep.mode = EPI_RESID; a.ep.resid = w.x; a.ep.out = w.x;      // x = res + scale * pw_conv2(.)  (scale folded)
+    launch_conv1d(a, s);
+  }
+  l.gamma = h->voc_norm_post.g; l.beta = h->voc_norm_post.b;
+  launch_layernorm(l, s);
+  a = conv_args(h->voc_out, w.x, (long long)vc * F, F, B, F);
+  a.ep.out = w.spec;
+  launch_conv1d(a, s);
+  launch_vocos_spec(w.spec, B, c.vocos_out_channels / 2, F, s);
+  a = conv_args(h->voc_idft, w.spec, (long long)c.vocos_out_channels * F, F, B, F);
+  a.ep.out = w.frames;
+  launch_conv1d(a, s);
+  launch_istft_overlap_add(w.frames, audio, B, c.vocos_n_fft, c.vocos_hop_length, F, s);
+  CHECK_LAUNCH();
+  return 0;
+}
+
 static size_t gen_layout(wetts_vits_t h, int B, int T, Arena& A, GenWs* w) {
   const wetts_vits_config& c = h->cfg;
+  if (c.vocoder_type == 1) {
+    VocosWs vw;
+    return vocos_layout(c, B, T, A, &vw);
+  }
   size_t mx = (size_t)c.upsample_initial_channel * T;
   size_t ch = c.upsample_initial_channel, len = T;
   for (int i = 0; i < c.n_upsamples; ++i) {
@@ -1140,6 +1350,9 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
   CHECK_READY(h);
   if (B <= 0 || T <= 0) return fail("empty batch");
   if (z_channel_stride < T || z_channel_stride > 0x7fffffff) return fail("bad channel stride");
+  if (h->cfg.vocoder_type == 1)
+    return vocos_forward(h, z, z_batch_stride, z_channel_stride, y_lengths, g, B, T, audio, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
   const wetts_vits_config& c = h->cfg;
   cudaStream_t s = (cudaStream_t)stream;
   Arena A(workspace, workspace_bytes);

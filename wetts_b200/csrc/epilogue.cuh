@@ -6,6 +6,7 @@
 namespace wetts {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf_acc(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // bias (+ per-(b,co) conditioning for EPI_PLAIN) of packed output channel `co`
 __device__ __forceinline__ float channel_term(const ConvArgs& a, int b, int co) {
@@ -55,6 +56,7 @@ __device__ __forceinline__ void epilogue_finish(const ConvArgs& a, int b, int co
   switch (e.mode) {
     case EPI_PLAIN:
       if (e.act == 1) v = fmaxf(v, 0.f);
+      else if (e.act == 2) v = gelu_erf_acc(v);
       if (e.out_mask) v *= msk;
       e.out[off] = v;
       break;

@@ -27,7 +27,7 @@ struct ConvEpilogue {
   const float* cond = nullptr;   // per (b, co) additive term, cond[b*cond_bs + cond_off + co]
   int cond_bs = 0;
   int cond_off = 0;
-  int act = 0;               // 0 none, 1 relu
+  int act = 0;               // 0 none, 1 relu, 2 gelu (erf)
   int out_mask = 0;          // multiply result by (t < lengths[b])
   int acc_mode = 0;          // EPI_MRF
   float div = 1.f;           // EPI_MRF final divisor
@@ -211,6 +211,18 @@ int tc_conv_install_fault_word(unsigned int* word);
 int tc16_conv_install_fault_word(unsigned int* word);
 int fused_rb_install_fault_word(unsigned int* word);
 int fused_mrf16_install_fault_word(unsigned int* word);
+
+// ---------------------------------------------------------------- Vocos / VITS2 helpers
+void launch_reflect_pad_left(const float* in, long long in_bs, int in_cs, const long long* lengths, float* out, int B, int C,
+                             int T, cudaStream_t s);
+void launch_gather_channels(const float* in, long long in_bs, int c0, int cstep, const long long* lengths, float* out,
+                            float* out_masked, int B, int C, int T, cudaStream_t s);
+void launch_vocos_spec(float* x, int B, int K, int F, cudaStream_t s);
+void launch_idft_weight(float* w /*[N][N+2][1]*/, int N, cudaStream_t s);
+void launch_istft_overlap_add(const float* frames /*[B][N][F]*/, float* out /*[B][hop*(F-1)]*/, int B, int N, int hop, int F,
+                              cudaStream_t s);
+void launch_scale_rows(const float* w, const float* bias, const float* sc, float* w_out, float* b_out, int rows, int cols,
+                       cudaStream_t s);
 
 unsigned long long kernel_launch_counter();
 void count_launch();

@@ -113,10 +113,11 @@ __global__ void speaker_embed_kernel(const long long* __restrict__ sid, const fl
 }
 
 // ------------------------------------------------------------------ channel LayerNorm
-constexpr int kLnMaxPerThread = 32;  // C <= 8 * 32
+// PT = channels per thread: 32 (C <= 256, every reference LayerNorm of the HiFi-GAN recipes) or 64 (C <= 512, Vocos)
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
+template <int kLnMaxPerThread>
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
   // block = 32 time steps x 8 channel groups; channel c handled by warp (c % 8)
   __shared__ float red[8][33];
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kAttThreads) rel_attention_kernel(const float*
   for (int idx = tid; idx < kAttQ * nrel; idx += kAttThreads) {
     const int i = idx / nrel, r = idx - i * nrel;
     const int ig_ = i0 + i, j = ig_ + r - window;
-    if (ig_ < T && j >= 0 && j < T) {
+    if (emb_k && ig_ < T && j >= 0 && j < T) {      // emb_k == nullptr: plain attention (window_size=None)
       float s = 0.f;
       for (int d = 0; d < dk; ++d) s = fmaf(qs[d * kAttQ + i], emb_k[r * dk + d], s);
       S[i * Tpad + j] += s;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(kAttThreads) rel_attention_kernel(const float*
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int i = qg * 4 + q, ig_ = i0 + i;
-    if (ig_ < T) {
+    if (ig_ < T && emb_v) {
       for (int r = 0; r < nrel; ++r) {
         const int j = ig_ + r - window;
         if (j < 0 || j >= T) continue;
@@ -331,6 +332,83 @@ __global__ void __launch_bounds__(kAttThreads) rel_attention_kernel(const float*
     const int d = idx / kAttQ, i = idx - d * kAttQ;
     if (i0 + i < T) ob[(long long)d * T + i0 + i] = os[idx];
   }
+}
+
+// ------------------------------------------------------------------ Vocos / VITS2 helpers
+// out[b][c][j] = in[b][c][j == 0 ? 1 : j - 1] * (src < len)    (nn.ReflectionPad1d([1, 0]) after the frame mask)
+__global__ void reflect_pad_left_kernel(const float* __restrict__ in, long long in_bs, int in_cs, const long long* __restrict__ lengths,
+                                        float* __restrict__ out, int C, int T) {
+  const int b = blockIdx.z, c = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > T) return;
+  const int src = (j == 0) ? (T > 1 ? 1 : 0) : j - 1;
+  float v = in[(long long)b * in_bs + (long long)c * in_cs + src];
+  if (lengths && src >= lengths[b]) v = 0.f;
+  out[((long long)b * C + c) * (T + 1) + j] = v;
+}
+// out[b][c][t] = in[b][c0 + c*cstep][t] (optionally * (t < len)): a channel slice / reversal of z (Flip folded in)
+__global__ void gather_channels_kernel(const float* __restrict__ in, long long in_bs, int c0, int cstep,
+                                       const long long* __restrict__ lengths, float* __restrict__ out, float* __restrict__ out_masked,
+                                       int C, int T) {
+  const int b = blockIdx.z, c = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  const float v = in[(long long)b * in_bs + (long long)(c0 + c * cstep) * T + t];
+  const long long o = ((long long)b * C + c) * T + t;
+  if (out) out[o] = v;
+  if (out_masked) out_masked[o] = (lengths && t >= lengths[b]) ? 0.f : v;
+}
+// x [B][2K][F] (log-magnitudes, phases) -> in place [re | im]: mag = min(exp(m), 100)  (decoders.py:300-305)
+__global__ void vocos_spec_kernel(float* __restrict__ x, int K, int F) {
+  const int b = blockIdx.z, k = blockIdx.y, f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  float* pm = x + ((long long)b * 2 * K + k) * F + f;
+  float* pp = pm + (long long)K * F;
+  const float mag = fminf(expf(*pm), 100.f);
+  float sn, cs;
+  sincosf(*pp, &sn, &cs);
+  *pm = mag * cs;
+  *pp = mag * sn;
+}
+// inverse real DFT + synthesis window as a 1x1 conv weight [N][2K][1] (K = N/2 + 1): row n, column k (re) / K + k (im)
+__global__ void idft_weight_kernel(float* __restrict__ w, int N) {
+  const int K = N / 2 + 1;
+  const long long total = (long long)N * 2 * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % (2 * K)), n = (int)(i / (2 * K));
+    const int k = col < K ? col : col - K;
+    const double ck = (k == 0 || k == N / 2) ? 1.0 : 2.0;
+    const long long kn = ((long long)k * n) % N;                       // exact angle reduction
+    const double ang = 6.283185307179586476925286766559 * (double)kn / (double)N;
+    const double win = 0.5 - 0.5 * cos(6.283185307179586476925286766559 * (double)n / (double)N);   // periodic hann
+    double v = (col < K) ? ck * cos(ang) : ((k == 0 || k == N / 2) ? 0.0 : -ck * sin(ang));
+    w[i] = (float)(v * win / (double)N);
+  }
+}
+// out[b][t] = sum_f frames[b][t + N/2 - f*hop][f] / sum_f win^2[t + N/2 - f*hop],  t < hop * (F - 1)   (torch.istft, center)
+__global__ void istft_overlap_add_kernel(const float* __restrict__ frames, float* __restrict__ out, int N, int hop, int F) {
+  const int b = blockIdx.y;
+  const long long L = (long long)hop * (F - 1);
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  const long long s = t + N / 2;
+  int f_hi = (int)(s / hop);
+  if (f_hi > F - 1) f_hi = F - 1;
+  float acc = 0.f, env = 0.f;
+  for (int f = f_hi; f >= 0; --f) {
+    const long long n = s - (long long)f * hop;
+    if (n >= N) break;
+    acc += frames[((long long)b * N + n) * F + f];
+    const float wv = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)N);
+    env = fmaf(wv, wv, env);
+  }
+  out[(long long)b * L + t] = acc / env;
+}
+// w[r][*] *= s[r], b[r] *= s[r]   (ConvNeXt layer scale folded into pw_conv2, decoders.py:245)
+__global__ void scale_rows_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ s,
+                                  float* __restrict__ w_out, float* __restrict__ b_out, int rows, int cols) {
+  const long long total = (long long)rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    w_out[i] = w[i] * s[i / cols];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) b_out[r] = bias[r] * s[r];
 }
 
 // ------------------------------------------------------------------ SDP pieces
@@ -609,7 +687,8 @@ void launch_speaker_embed(const long long* sid, const float* table, float* g, in
 }
 void launch_layernorm(const LnArgs& a, cudaStream_t s) {
   dim3 grid((a.T + 31) / 32, a.B);
-  layernorm_kernel<<<grid, 256, 0, s>>>(a);
+  if (a.C <= 256) layernorm_kernel<32><<<grid, 256, 0, s>>>(a);
+  else layernorm_kernel<64><<<grid, 256, 0, s>>>(a);
   count_launch();
 }
 void launch_rel_attention(const float* qkv, const float* emb_k, const float* emb_v, const long long* lengths, float* out,
@@ -714,6 +793,39 @@ void launch_audio_to_int16(const float* audio, const long long* lengths, int B, 
 void launch_transpose_blc(const float* in, float* out, int B, int L, int C, cudaStream_t s) {
   dim3 grid((L + 31) / 32, (C + 31) / 32, B);
   transpose_blc_kernel<<<grid, dim3(32, 8), 0, s>>>(in, out, L, C);
+  count_launch();
+}
+
+void launch_reflect_pad_left(const float* in, long long in_bs, int in_cs, const long long* lengths, float* out, int B, int C,
+                             int T, cudaStream_t s) {
+  dim3 grid((T + 1 + 127) / 128, C, B);
+  reflect_pad_left_kernel<<<grid, 128, 0, s>>>(in, in_bs, in_cs, lengths, out, C, T);
+  count_launch();
+}
+void launch_gather_channels(const float* in, long long in_bs, int c0, int cstep, const long long* lengths, float* out,
+                            float* out_masked, int B, int C, int T, cudaStream_t s) {
+  dim3 grid((T + 127) / 128, C, B);
+  gather_channels_kernel<<<grid, 128, 0, s>>>(in, in_bs, c0, cstep, lengths, out, out_masked, C, T);
+  count_launch();
+}
+void launch_vocos_spec(float* x, int B, int K, int F, cudaStream_t s) {
+  dim3 grid((F + 127) / 128, K, B);
+  vocos_spec_kernel<<<grid, 128, 0, s>>>(x, K, F);
+  count_launch();
+}
+void launch_idft_weight(float* w, int N, cudaStream_t s) {
+  idft_weight_kernel<<<1024, 256, 0, s>>>(w, N);
+  count_launch();
+}
+void launch_istft_overlap_add(const float* frames, float* out, int B, int N, int hop, int F, cudaStream_t s) {
+  const long long L = (long long)hop * (F - 1);
+  dim3 grid((unsigned)((L + 255) / 256), B);
+  istft_overlap_add_kernel<<<grid, 256, 0, s>>>(frames, out, N, hop, F);
+  count_launch();
+}
+void launch_scale_rows(const float* w, const float* bias, const float* sc, float* w_out, float* b_out, int rows, int cols,
+                       cudaStream_t s) {
+  scale_rows_kernel<<<256, 256, 0, s>>>(w, bias, sc, w_out, b_out, rows, cols);
   count_launch();
 }
 

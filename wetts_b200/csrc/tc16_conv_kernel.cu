@@ -55,6 +55,7 @@ __device__ __forceinline__ void tc16_epilogue_slice(const ConvArgs& a, int b, in
       for (int i = 0; i < 16; ++i) {
         float x = v[i];
         if (e.act == 1) x = fmaxf(x, 0.f);
+        else if (e.act == 2) x = gelu_erf_acc(x);
         if (e.out_mask) x *= msk;
         if (i < nval) op[(size_t)i * Ts] = x;
       }

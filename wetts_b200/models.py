@@ -122,6 +122,8 @@ class _Engine:
 
     @property
     def upsample(self):
+        if self.cfg.vocoder_type == 1:
+            return int(self.cfg.vocos_hop_length)
         u = 1
         for i in range(self.cfg.n_upsamples):
             u *= self.cfg.upsample_rates[i]
@@ -242,11 +244,15 @@ class SynthesizerTrn:
     def __init__(self, n_vocab, spec_channels, segment_size, inter_channels, hidden_channels, filter_channels,
                  n_heads, n_layers, kernel_size, p_dropout, resblock, resblock_kernel_sizes, resblock_dilation_sizes,
                  upsample_rates, upsample_initial_channel, upsample_kernel_sizes, n_speakers=0, gin_channels=0,
-                 use_sdp=True, vocoder_type="hifigan", **kwargs):
-        if vocoder_type != "hifigan":
-            raise NotImplementedError("only the HiFi-GAN generator is on the accelerated path (Vocos: SURVEY.md §8f rank 4)")
-        if kwargs.get("use_transformer_flows", False):
-            raise NotImplementedError("VITS2 transformer flows are out of scope (SURVEY.md §8f rank 4)")
+                 use_sdp=True, vocoder_type="hifigan", vocos_channels=512, vocos_h_channels=1536, vocos_out_channels=1026,
+                 vocos_num_layers=8, vocos_istft_config=None, **kwargs):
+        if vocoder_type not in ("hifigan", "vocos"):
+            raise NotImplementedError(f"vocoder_type {vocoder_type!r}: only 'hifigan' and 'vocos' exist in the reference")
+        self.use_transformer_flows = bool(kwargs.get("use_transformer_flows", False))
+        self.transformer_flow_type = kwargs.get("transformer_flow_type", "mono_layer_post_residual")
+        if self.use_transformer_flows and self.transformer_flow_type != "pre_conv":
+            raise NotImplementedError("of the VITS2 transformer flows only 'pre_conv' (the vits2_vocos_v1 recipe) is built "
+                                      "(SURVEY.md §8f rank 4)")
         if kwargs.get("use_spk_conditioned_encoder", False):
             raise NotImplementedError("speaker-conditioned text encoder is not used by the v1/v2/v3 recipes")
         self.n_vocab, self.spec_channels, self.segment_size = n_vocab, spec_channels, segment_size
@@ -275,6 +281,17 @@ class SynthesizerTrn:
         for i, (u, k) in enumerate(zip(self.upsample_rates, self.upsample_kernel_sizes)):
             c.upsample_rates[i], c.upsample_kernel_sizes[i] = u, k
         c.upsample_initial_channel = upsample_initial_channel
+        self.vocoder_type = vocoder_type
+        if vocoder_type == "vocos":
+            ic = dict(vocos_istft_config or {"n_fft": 1024, "hop_length": 256, "win_length": 1024, "center": True})
+            if hasattr(vocos_istft_config, "to_dict"):
+                ic = vocos_istft_config.to_dict()
+            if ic.get("win_length", ic["n_fft"]) != ic["n_fft"] or not ic.get("center", True):
+                raise NotImplementedError("Vocos iSTFT: only win_length == n_fft with center=True (the reference recipe)")
+            c.vocoder_type = 1
+            c.vocos_channels, c.vocos_h_channels, c.vocos_out_channels = vocos_channels, vocos_h_channels, vocos_out_channels
+            c.vocos_num_layers, c.vocos_n_fft, c.vocos_hop_length = vocos_num_layers, ic["n_fft"], ic["hop_length"]
+        c.flow_type = 1 if self.use_transformer_flows else 0
         self._engine = _Engine(c)
         self.enc_p = TextEncoder(self._engine)
         self.dp = DurationPredictorBlock(self._engine)

@@ -73,16 +73,36 @@ def state_dict_spec(hps_model, n_vocab, n_speakers):
         ln(f"enc_p.encoder.norm_layers_2.{i}", H)
     conv("enc_p.proj", 2 * inter, H, 1)
 
+    vocos = m.get("vocoder_type", "hifigan") == "vocos"
+    if vocos:
+        # Vocos generator (decoders.py:250-282): in_conv, cond, norm_pre, ConvNeXt layers (:221-247), norm_post, out_conv
+        vc, vh, vo = m.get("vocos_channels", 512), m.get("vocos_h_channels", 1536), m.get("vocos_out_channels", 1026)
+        conv("dec.in_conv", vc, inter, 1)
+        if gin:
+            conv("dec.cond", vc, gin, 1)
+        ln("dec.norm_pre", vc)
+        for i in range(m.get("vocos_num_layers", 8)):
+            p = f"dec.layers.{i}"
+            conv(p + ".dw_conv", vc, 1, 3)
+            ln(p + ".norm", vc)
+            conv(p + ".pw_conv1", vh, vc, 1)
+            conv(p + ".pw_conv2", vc, vh, 1)
+            spec.append((p + ".scale", (1, vc, 1), "scale"))
+        ln("dec.norm_post", vc)
+        conv("dec.out_conv", vo, vc, 1, kind="out_small")
     # HiFi-GAN generator (decoders.py:28-61)
     c0 = m["upsample_initial_channel"]
-    conv("dec.conv_pre", c0, inter, 7)
+    if not vocos:
+        conv("dec.conv_pre", c0, inter, 7)
     ch = c0
     for i, (u, k) in enumerate(zip(m["upsample_rates"], m["upsample_kernel_sizes"])):
+        if vocos:
+            break
         cin, cout = c0 // (2 ** i), c0 // (2 ** (i + 1))
         wn_conv(f"dec.ups.{i}", cin, cout, k, cout)  # ConvTranspose1d: [C_in, C_out, k]
         ch = cout
     rb = 0
-    for i in range(len(m["upsample_rates"])):
+    for i in range(0 if vocos else len(m["upsample_rates"])):
         ch = c0 // (2 ** (i + 1))
         for k, dil in zip(m["resblock_kernel_sizes"], m["resblock_dilation_sizes"]):
             p = f"dec.resblocks.{rb}"
@@ -95,14 +115,29 @@ def state_dict_spec(hps_model, n_vocab, n_speakers):
                 for j in range(len(dil)):
                     wn_conv(f"{p}.convs.{j}", ch, ch, k, ch)
             rb += 1
-    conv("dec.conv_post", 1, ch, 7, bias=False)
-    if gin:
-        conv("dec.cond", c0, gin, 1)
+    if not vocos:
+        conv("dec.conv_post", 1, ch, 7, bias=False)
+        if gin:
+            conv("dec.cond", c0, gin, 1)
 
     # flow: 4 residual coupling layers at even indices (flows.py:417-428, modules.py:33-58)
     half = inter // 2
+    tflow = m.get("use_transformer_flows", False)
+    if tflow and m.get("transformer_flow_type", "mono_layer_post_residual") != "pre_conv":
+        raise NotImplementedError("only the 'pre_conv' transformer flow of the vits2_vocos_v1 recipe is supported")
     for f in (0, 2, 4, 6):
         p = f"flow.flows.{f}"
+        if tflow:
+            # ResidualCouplingTransformersLayer.pre_transformer (flows.py:112-120): Encoder(96, 96, heads 2, layers 2, k 3,
+            # window_size=None -> no relative-position tables)
+            for i in range(2):
+                a = f"{p}.pre_transformer.attn_layers.{i}"
+                for n in ("conv_q", "conv_k", "conv_v", "conv_o"):
+                    conv(f"{a}.{n}", half, half, 1)
+                ln(f"{p}.pre_transformer.norm_layers_1.{i}", half)
+                conv(f"{p}.pre_transformer.ffn_layers.{i}.conv_1", half, half, 3)
+                conv(f"{p}.pre_transformer.ffn_layers.{i}.conv_2", half, half, 3)
+                ln(f"{p}.pre_transformer.norm_layers_2.{i}", half)
         conv(p + ".pre", H, half, 1)
         for i in range(4):
             wn_conv(f"{p}.enc.in_layers.{i}", 2 * H, H, 5, 2 * H)
@@ -198,6 +233,11 @@ def make_state_dict(hps_model, n_vocab, n_speakers, seed=1234):
             t = 0.1 * randn(shape)
         elif kind == "small":
             t = 0.02 * randn(shape)
+        elif kind == "scale":        # ConvNeXt layer scale (decoders.py:235-237: 1 / num_layers), perturbed
+            t = (1.0 / 8.0) * (1.0 + 0.3 * randn(shape))
+        elif kind == "out_small":    # Vocos out_conv: log-magnitudes and phases; keep exp(mag) moderate
+            fan_in = shape[1] * shape[2]
+            t = uniform(shape, 0.5 / math.sqrt(fan_in))
         elif kind == "spk":
             t = randn(shape)
         else:
