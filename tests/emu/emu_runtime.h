@@ -209,6 +209,7 @@ WETTS_DEVICE void cta_sync() { emu::cta()->cta_bar->arrive_and_wait(); }
 WETTS_DEVICE void warp_sync() { emu::cta()->warp_bars[emu::g_tid >> 5]->arrive_and_wait(); }
 WETTS_DEVICE float ldg(const float* p) { return *p; }
 WETTS_DEVICE long long clock_now() { return 0; }
+WETTS_DEVICE void spin_cycles(long long) {}
 WETTS_DEVICE void trap_now() { emu::die("kernel trap"); }
 WETTS_DEVICE int ldg_i32(const int* p) { return *p; }
 WETTS_DEVICE float4 ldg4(const float* p) {

@@ -121,6 +121,7 @@ def test_text_encoder_with_tensor_core_attention(name):
     import wetts_b200
     hps, sd, g, t = load_case(name)
     net = wetts_b200.build_model(hps, int(g["n_vocab"]), int(g["n_speakers"]), sd, "cuda")
+    net.set_option("attention_tensor_cores", 0)
     h0, m0, l0, _ = net.enc_p(t["x"], t["x_lengths"])
     n0 = net.launch_count()
     net.set_option("attention_tensor_cores", 1)

@@ -25,11 +25,11 @@ static thread_local std::string g_err;
 // (wetts_vits_set_option), else the process-wide default (wetts_set_option).  Set by CHECK_READY.
 struct CallOpts {
   bool tc = true, fused = true, len_aware = false;
-  int fmt = 32;   // operand format of the fused stage kernels: 32 = 3xTF32 (kind::tf32), 16 = f16 split (kind::f16)
+  int fmt = 16;   // operand format of the tensor-pipe kernels: 32 = 3xTF32 (kind::tf32), 16 = f16 split (kind::f16)
   bool attn_tc = false;
 };
-static std::atomic<int> g_tensor_format{32};
-static std::atomic<int> g_attn_tc{0};   // text-encoder attention on the tensor pipe (attn_tc.cu) for 64 <= Tx <= 128
+static std::atomic<int> g_tensor_format{16};
+static std::atomic<int> g_attn_tc{1};   // text-encoder attention on the tensor pipe (attn_tc.cu) for 64 <= Tx <= 128
 
 // Host-visible fault word of the device-side soft watchdog (tc_prims.cuh mbar_wait): one mapped pinned word per
 // process, installed on every device a handle is created on.

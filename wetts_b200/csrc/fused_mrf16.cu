@@ -106,11 +106,12 @@ static int launch_variant(const FusedMrfArgs& a, int grid, size_t smem, cudaStre
 // CTAs per SM: the accumulators are reused by every conv (4N TMEM columns) and the f16 tiles are half the size of the
 // tf32 ones, so the ResBlock2 kernels fit 3 (C = 32) / 2... CTAs; co-resident CTAs overlap one CTA's SIMT phases with
 // another's MMAs.  WETTS_MRF16_CTAS overrides (experiments).
+static const int g_c64_ctas = getenv("WETTS_MRF16_C64_CTAS") ? atoi(getenv("WETTS_MRF16_C64_CTAS")) : 1;
 static int ctas_per_sm(int C, int type) {
   static const int forced = getenv("WETTS_MRF16_CTAS") ? atoi(getenv("WETTS_MRF16_CTAS")) : 0;
   if (forced > 0) return forced;
   if (C == 32) return type == 2 ? 3 : 2;
-  return 1;
+  return (type == 2) ? g_c64_ctas : 1;
 }
 
 template <bool PROFILE>
@@ -120,6 +121,7 @@ static int launch_any(int C, int type, int ring, int per_sm, const FusedMrfArgs&
     if (per_sm >= 3) return ring == 6 ? V(32, 256, 3, 6, 225, false) : V(32, 256, 3, 4, 225, false);
     return ring == 6 ? V(32, 256, 2, 6, 225, false) : V(32, 256, 2, 4, 225, false);
   }
+  if (type == 2 && C == 64 && per_sm >= 2) return ring == 6 ? V(64, 256, 2, 6, 225, false) : V(64, 256, 2, 4, 225, false);
   if (type == 2 && C == 64) return ring == 6 ? V(64, 512, 1, 6, 225, false) : V(64, 512, 1, 4, 225, false);
   if (type == 1 && C == 32) return ring == 6 ? V(32, 256, 2, 6, 249, true) : V(32, 256, 2, 4, 249, true);
   if (type == 1 && C == 64) return ring == 6 ? V(64, 512, 1, 6, 249, true) : V(64, 512, 1, 4, 249, true);
@@ -172,6 +174,9 @@ int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
   const size_t smem = fused_mrf16_smem_bytes(C, ring, rp, a.type == 1 ? 2 : 1);
   const long long items = (long long)a.B * ((a.T + 127) / 128);   // upper bound in the length-aware mode
   const int per_sm = ctas_per_sm(C, a.type);
+  static const int stagger = getenv("WETTS_MRF16_STAGGER") ? atoi(getenv("WETTS_MRF16_STAGGER")) : 0;
+  a.stagger = per_sm > 1 ? stagger : 0;
+  a.n_sm = n_sm;
   const int grid = (int)(items < (long long)per_sm * n_sm ? items : (long long)per_sm * n_sm);
   if (getenv("WETTS_FUSED_RB_PROFILE")) return launch_profiled(C, a.type, ring, per_sm, a, grid, smem, items, s);
   return launch_any<false>(C, a.type, ring, per_sm, a, grid, smem, s);

@@ -38,6 +38,9 @@ struct FusedMrfArgs {
   // tile of every utterance, in (b, tile) order
   const int2_t* item_map = nullptr;
   const int* n_items_dev = nullptr;
+  // start-up stagger (cycles) of the k-th co-resident CTA of an SM (k = block index / n_sm): co-resident CTAs that
+  // start together fall into a convoy (all in their MMA phase, then all in their SIMT phase); 0 = off
+  int stagger = 0, n_sm = 1;
   long long* prof = nullptr;    // profiling instantiation only
 };
 

@@ -61,7 +61,10 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   // warps 0 (MMA issuer) and 1 (weight producer) stay out of the staging when the other warps cover the tile
   constexpr int SW0 = (UNITS <= THREADS - 64) ? 2 : 0;
   constexpr int STHREADS = THREADS - 32 * SW0;
-  static_assert(UNITS <= STHREADS, "one staging unit per thread");
+  // one staging unit per thread: its 8 loads are prefetched into registers during the previous MMA phase; more units
+  // than threads (C = 64 with 256 threads): NU units per thread, loaded and stored inside the staging phase
+  constexpr bool PREFETCH = (UNITS <= STHREADS);
+  constexpr int NU = (UNITS + STHREADS - 1) / STHREADS;
   constexpr uint32_t A_HALF = (uint32_t)CG8 * RP * 16u;         // bytes of the hi (or lo') tile
   constexpr uint32_t TILE_BYTES = 2u * A_HALF;
   constexpr int NBIAS = kMrfMaxRb * kMrfMaxConv;
@@ -128,6 +131,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   float4 pf[8];
   const int su = tid - 32 * SW0;                       // staging unit of this thread (negative: not a staging thread)
   auto prefetch = [&](int item, int j) {
+    if (!PREFETCH) return;
     if (su < 0 || su >= UNITS) return;
     int b, t0;
     decode(item, b, t0);
@@ -153,12 +157,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + A_HALF) = lo;
   };
-  auto stage = [&](int j) {
-    if (su < 0 || su >= UNITS) return;
-    const int Hp = (halo_of(j) + 3) & ~3;
-    const int Q = (128 + 2 * Hp) >> 2;
-    const int cg = su & (CG8 - 1), q = su >> LOG_CG8;
-    if (q >= Q) return;
+  auto store_unit = [&](int cg, int q) {
     float y[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = lrelu(pf[e].x);
@@ -172,6 +171,32 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
 #pragma unroll
     for (int e = 0; e < 8; ++e) y[e] = lrelu(pf[e].w);
     split_store8(Xt, cg, 4 * q + 3, y);
+  };
+  auto stage = [&](int item, int j) {
+    if (su < 0) return;
+    const int Hp = (halo_of(j) + 3) & ~3;
+    const int Q = (128 + 2 * Hp) >> 2;
+    if (PREFETCH) {
+      if (su >= UNITS) return;
+      const int cg = su & (CG8 - 1), q = su >> LOG_CG8;
+      if (q < Q) store_unit(cg, q);
+    } else {
+      int b, t0;
+      decode(item, b, t0);
+#pragma unroll 1
+      for (int i = 0; i < NU; ++i) {
+        const int u = su + i * STHREADS;
+        const int cg = u & (CG8 - 1), q = u >> LOG_CG8;
+        if (u < UNITS && q < Q) {
+          const int t = t0 - Hp + 4 * q;
+          const bool ok = (t >= 0) && (t < T);
+          const float* src = p.in + (long long)b * bs + (long long)(8 * cg) * T + t;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) pf[e] = ok ? ldg4(src + (long long)e * T) : float4{0.f, 0.f, 0.f, 0.f};
+          store_unit(cg, q);
+        }
+      }
+    }
   };
   // pre-activation values of 8 channels recovered from the staged hi / lo' pair of (row r, channel group cg)
   auto staged_value8 = [&](const uint8_t* tile, int cg, int r, float* x) {
@@ -299,6 +324,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
       t_prev = now;
     }
   };
+  if (p.stagger > 0) spin_cycles((long long)(WETTS_BID / p.n_sm) * p.stagger);
   if (my_items > 0) prefetch(WETTS_BID, 0);
 
   for (int it = 0; it < my_items; ++it) {
@@ -319,7 +345,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
       const int next_j = (j + 1 < nrb) ? j + 1 : 0;
 
       mark(8);
-      stage(j);
+      stage(item, j);
       fence_async_smem();
       mark(0);
       tc_fence_before();

@@ -254,6 +254,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
     // on the tile count, cost the issue loop its uniform datapath: R2UR 19 -> 162).
     int tiles = min(G, (T - t_group0 + MT - 1) / MT);
     if (a.la_len) tiles = ((long long)t_group0 >= (a.la_len[b] + a.la_margin) * (long long)a.la_rate) ? 0 : tiles;
+    // a zero-tile item must not touch the weight pipeline either (the next chunk's prefetch is issued from inside the
+    // tile loop): it runs zero chunks; only the per-item barriers tick
+    const int n_chunks_item = (tiles > 0) ? p.n_chunks : 0;
     const long long len = a.lengths ? a.lengths[b] : (long long)T;
     // per-item additive term of every output channel (bias + speaker conditioning), double buffered
     float* av = addv + (item_count & 1) * 256;
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
       constexpr int iw = 0;   // NI == 1: the issuer index is a constant, not a function of the warp index
       static_assert(NI == 1, "one issuing warp");
       {
-        for (int c = 0; c < p.n_chunks; ++c) {
+        for (int c = 0; c < n_chunks_item; ++c) {
           int bb = 0;
           bool load_b = true;
           if (p.n_chunks == 1) {
@@ -369,7 +372,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc_kernel(const TcCo
       const int Tin = a.in_T > 0 ? a.in_T : T;
       const int t_hi = a.in_mask ? (int)(len < Tin ? len : Tin) : Tin;
       const float* in_b = a.in + (long long)b * a.in_bs;
-      for (int c = 0; c < p.n_chunks; ++c) {
+      for (int c = 0; c < n_chunks_item; ++c) {
         const int c0 = c * KC;
         const bool fast = full16 && (a.Cin - c0) >= KC;
         for (int g = 0; g < tiles; ++g) {

@@ -31,6 +31,10 @@ WETTS_DEVICE void cta_sync() { __syncthreads(); }
 WETTS_DEVICE void warp_sync() { __syncwarp(); }
 WETTS_DEVICE float ldg(const float* p) { return __ldg(p); }
 WETTS_DEVICE long long clock_now() { return clock64(); }
+WETTS_DEVICE void spin_cycles(long long n) {     // busy-wait n SM cycles (start-up stagger of co-resident CTAs)
+  const long long t0 = clock64();
+  while (clock64() - t0 < n) {}
+}
 WETTS_DEVICE void trap_now() { __trap(); }
 WETTS_DEVICE float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 WETTS_DEVICE int ldg_i32(const int* p) { return __ldg(p); }
