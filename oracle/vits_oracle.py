@@ -39,6 +39,11 @@ def fold_weight_norm(sd):
     return out
 
 
+def _plain(cfg):
+    """the model section as a plain dict (accepts the HParams attribute bag, which has no .get)"""
+    return cfg.to_dict() if hasattr(cfg, "to_dict") else cfg
+
+
 def seq_mask(lengths, max_len):
     """commons.py:113-117"""
     return (torch.arange(max_len)[None, :] < lengths[:, None]).to(torch.float32)
@@ -295,6 +300,7 @@ def wn(w, prefix, x, m3, g, H, n_layers=4):
 
 def flow_reverse(w, cfg, z, y_m3, g):
     """flows.py:442-449 reversed list + flows.py:494-513 (mean_only, reverse)."""
+    cfg = _plain(cfg)
     H = cfg["hidden_channels"]
     half = cfg["inter_channels"] // 2
     tflow = cfg.get("use_transformer_flows", False)      # 'pre_conv' type: flows.py:89-176
@@ -340,6 +346,7 @@ def istft_hann(re, im, n_fft, hop):
 
 def vocos_generator(w, cfg, z, g):
     """VocosGenerator.forward (decoders.py:287-307) with ConvNeXtLayer.forward (:239-247)."""
+    cfg = _plain(cfg)
     x = F.pad(z, (1, 0), mode="reflect")
     x = F.conv1d(x, w["dec.in_conv.weight"], w["dec.in_conv.bias"])
     if g is not None:
@@ -365,6 +372,7 @@ def vocos_generator(w, cfg, z, g):
 # --------------------------------------------------------------------------- generator
 def generator(w, cfg, z, g):
     """decoders.py:63-82 + ResBlock1 :157-170 / ResBlock2 :205-214."""
+    cfg = _plain(cfg)
     if cfg.get("vocoder_type", "hifigan") == "vocos":
         return vocos_generator(w, cfg, z, g)
     x = F.conv1d(z, w["dec.conv_pre.weight"], w["dec.conv_pre.bias"], padding=3)

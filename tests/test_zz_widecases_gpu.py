@@ -6,12 +6,17 @@ duration-predictor / flow / generator convolution takes the tcgen05 kernel at T 
   v3_tx128       configs[2]'s route: multilingual v3, DurationPredictor, ragged 128 / 97 / 64 phonemes
 
 All gating (no xfail).  Tolerances, relative to rms(reference) as everywhere: blocks 1e-4 (generator / flow 3e-4),
-end to end 1e-3, integer outputs exact -- including the frame counts from the GPU's OWN durations on the tcgen05 route.
-One documented exception: z_p = m_p + noise * exp(logs_p) * noise_scale multiplies an error in logs_p by up to
-|noise| * exp(logs_p) * 0.667 (11x on aishell3_long), and on the tensor pipe logs_p carries the accumulation error of
-a 768-channel k=3 conv chain (hundreds of sequential fp32 TMEM accumulations; measured 1e-5..3e-5 of rms where the fp32
-SIMT route has 2e-6, profiles/r02_tc_numerics.txt) -- so z_p is held to 3e-4, the same bound as the flow block, not
-1e-4.  The per-path errors are printed (-s) and committed under profiles/."""
+end to end 1e-3, integer outputs exact -- including the frame counts from the GPU's OWN durations on the tensor-core
+route.  Every case runs on both operand formats of the tensor-pipe kernels:
+  fmt16 (default): f16 split, K = 16 channels per MMA.  Measured on B200 (profiles/r02_tc_numerics.txt): text encoder
+         1.0e-5, z_p 3.2e-5 .. 3.4e-5, generator 3e-6 .. 1.4e-5 -- everything inside the 1e-4 block tolerance.
+  fmt32: 3xTF32, K = 8 per MMA: twice the sequential fp32 accumulations into TMEM, whose truncation is the dominant
+         error of the tensor route (profiles/r02_mma_numerics_and_rates.txt: it grows linearly with the number of
+         accumulations and halves when the accumulations are dealt over two accumulators).  Text encoder 5e-5 .. 6e-5;
+         z_p = m_p + noise * exp(logs_p) * noise_scale multiplies the error of logs_p by up to |noise| exp(logs_p) 0.667
+         (11x on aishell3_long): 1.5e-4 .. 2.1e-4, so z_p / z are held to 3e-4 on THIS format only.
+This is what round 1 could not explain (its CPU probe modelled the operand split, not the accumulation): not a staging
+or masking bug -- the fp32 SIMT route is at 3e-6 on the same inputs, the f16 route at 1e-5."""
 import pytest
 import torch
 
@@ -41,7 +46,7 @@ def test_wide_fixture_end_to_end_and_blocks(name, fmt):
     assert torch.equal(net.last_y_lengths.cpu(), t["y_lengths"])
     e_zp, e_z, e_o = rel_rms_err(z_p.cpu(), t["z_p"]), rel_rms_err(z.cpu(), t["z"]), rel_rms_err(o.cpu(), t["o"])
     print(f"{name}: e2e z_p {e_zp:.3e}  z {e_z:.3e}  o {e_o:.3e}")
-    assert e_zp < BLOCK_TOL * 3        # exp(logs_p) amplification, see the module docstring
+    assert e_zp < (BLOCK_TOL if fmt == 16 else BLOCK_TOL * 3)    # 3xTF32: accumulation error x exp(logs_p) amplification
     assert e_z < BLOCK_TOL * 3
     assert e_o < E2E_TOL
     a = attn[:, 0].cpu()
