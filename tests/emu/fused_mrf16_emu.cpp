@@ -157,6 +157,7 @@ int main(int argc, char** argv) {
     if (C == 64 && thr == 512 && ring == 6) RUN(64, 512, 6, 225, false);
     if (C == 64 && thr == 256 && ring == 6) RUN(64, 256, 6, 225, false);   // 2 units / 2 slices per thread
     if (C == 64 && thr == 256 && ring == 4) RUN(64, 256, 4, 225, false);
+    if (C == 128 && thr == 512 && ring == 4) RUN(128, 512, 4, 225, false);   // stage-0 width of the v3 generator
   } else {
     if (C == 32 && thr == 256 && ring == 4) RUN(32, 256, 4, 249, true);
     if (C == 32 && thr == 256 && ring == 6) RUN(32, 256, 6, 249, true);

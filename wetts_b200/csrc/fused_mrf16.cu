@@ -50,7 +50,10 @@ __global__ void mrf_item_map_kernel(const long long* __restrict__ lengths, int B
 }  // namespace
 
 bool fused_mrf16_supported(int C, int type, int nrb, const int* k, const int (*dil)[kMrfMaxConv], int nconv) {
-  if (C != 32 && C != 64) return false;
+  if (C != 32 && C != 64 && C != 128) return false;
+  if (C == 128 && type != 2) return false;      // ResBlock1 needs two tiles: 2 x 127 KB do not fit
+  static const int c128 = getenv("WETTS_MRF16_C128") ? atoi(getenv("WETTS_MRF16_C128")) : 0;   // opt-in until measured
+  if (C == 128 && !c128) return false;
   if (nrb < 1 || nrb > kMrfMaxRb) return false;
   if (!((type == 2 && nconv == 2) || (type == 1 && nconv == 6))) return false;
   const int rp = (type == 1) ? 249 : 225;
@@ -111,6 +114,7 @@ static int ctas_per_sm(int C, int type) {
   static const int forced = getenv("WETTS_MRF16_CTAS") ? atoi(getenv("WETTS_MRF16_CTAS")) : 0;
   if (forced > 0) return forced;
   if (C == 32) return type == 2 ? 3 : 2;
+  if (C == 128) return 1;
   return (type == 2) ? g_c64_ctas : 1;
 }
 
@@ -121,6 +125,7 @@ static int launch_any(int C, int type, int ring, int per_sm, const FusedMrfArgs&
     if (per_sm >= 3) return ring == 6 ? V(32, 256, 3, 6, 225, false) : V(32, 256, 3, 4, 225, false);
     return ring == 6 ? V(32, 256, 2, 6, 225, false) : V(32, 256, 2, 4, 225, false);
   }
+  if (type == 2 && C == 128) return ring == 6 ? V(128, 512, 1, 6, 225, false) : V(128, 512, 1, 4, 225, false);
   if (type == 2 && C == 64 && per_sm >= 2) return ring == 6 ? V(64, 256, 2, 6, 225, false) : V(64, 256, 2, 4, 225, false);
   if (type == 2 && C == 64) return ring == 6 ? V(64, 512, 1, 6, 225, false) : V(64, 512, 1, 4, 225, false);
   if (type == 1 && C == 32) return ring == 6 ? V(32, 256, 2, 6, 249, true) : V(32, 256, 2, 4, 249, true);
@@ -168,7 +173,8 @@ int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
   const int n_sm = current_device_sm_count();
   if (n_sm <= 0) return 1;
   const char* force = getenv("WETTS_FUSED_RB_RING");
-  const int ring = force ? atoi(force) : fused_mrf16_ring_slots(a.nq);
+  int ring = force ? atoi(force) : fused_mrf16_ring_slots(a.nq);
+  if (ring == 6 && fused_mrf16_smem_bytes(C, 6, (a.type == 1) ? 249 : 225, a.type == 1 ? 2 : 1) > 227 * 1024) ring = 4;
   if (ring != 4 && !(ring == 6 && a.nq % 6 == 0)) return 1;
   const int rp = (a.type == 1) ? 249 : 225;
   const size_t smem = fused_mrf16_smem_bytes(C, ring, rp, a.type == 1 ? 2 : 1);

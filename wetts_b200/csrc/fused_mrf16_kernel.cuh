@@ -44,7 +44,7 @@ namespace wetts {
 template <int C, int THREADS, int MINB, int NB, int RP, bool TWO_TILES, bool PROFILE = false>
 WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const FusedMrfArgs p) {
   using namespace tc;
-  static_assert(C == 32 || C == 64, "channel count");
+  static_assert(C == 32 || C == 64 || C == 128, "channel count");
   static_assert(NB == 4 || NB == 6, "ring size");
   static_assert((RP & 1) == 1 && RP >= 225, "odd row pitch");
   constexpr int N = C;
@@ -52,7 +52,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   constexpr uint32_t CHUNK_BYTES = 4u * 2u * N * 16u;          // [4 k-groups][hi | lo' : 2N rows][8 halfs]
   constexpr uint32_t TMEM_COLS = 4u * N;                        // two accumulator blocks x [hi*hi | small terms]
   constexpr int CG8 = C / 8;                                    // 8-channel groups of the activation tile
-  constexpr int LOG_CG8 = (CG8 == 4) ? 2 : 3;
+  constexpr int LOG_CG8 = (CG8 == 4) ? 2 : (CG8 == 8 ? 3 : 4);
   constexpr int NWARP = THREADS / 32, GRPS = NWARP / 4;         // warps sharing a TMEM lane quarter split the columns
   static_assert(NWARP % 4 == 0 && (C / 16) % GRPS == 0, "warps must tile the 128 x C accumulator block");
   constexpr int SL = (C / 16) / GRPS;                           // 16-channel slices per thread

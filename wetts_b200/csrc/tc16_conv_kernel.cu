@@ -206,27 +206,26 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
   const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 96);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 112);
   float* addv = reinterpret_cast<float*>(smem + 128);  // [2][N] bias + conditioning of the current item
   uint8_t* A0 = smem + 128 + 2 * 256 * 4;
   uint8_t* B0 = A0 + (size_t)na * a_bytes;
-  const uint32_t bar_a_free = smem_u32(&bars[0]);   // [2]  MMA -> workers: activation buffer reusable
-  const uint32_t bar_b_full = smem_u32(&bars[2]);   // [2]  TMA -> MMA: weight tile landed
-  const uint32_t bar_b_free = smem_u32(&bars[4]);   // [2]  MMA -> MMA: weight buffer reusable
-  const uint32_t bar_acc = smem_u32(&bars[6]);      //      MMA -> workers: accumulators complete
-  const uint32_t bar_a_full = smem_u32(&bars[8]);   // [2]  workers -> MMA: activation tile staged
+  const uint32_t bar_a_free = smem_u32(&bars[0]);   // [4]  MMA -> workers: activation buffer reusable
+  const uint32_t bar_b_full = smem_u32(&bars[4]);   // [2]  TMA -> MMA: weight tile landed
+  const uint32_t bar_b_free = smem_u32(&bars[6]);   // [2]  MMA -> MMA: weight buffer reusable
+  const uint32_t bar_acc = smem_u32(&bars[8]);      //      MMA -> workers: accumulators complete
+  const uint32_t bar_a_full = smem_u32(&bars[9]);   // [4]  workers -> MMA: activation tile staged
   const uint32_t A_addr = smem_u32(A0), B_addr = smem_u32(B0);
 
   if (warp == 0) {
     tmem_alloc(smem_u32(tmem_slot), tmem_cols);
   }
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&bars[i]), 1);   // a_free[2], b_full[2]
+    for (int i = 0; i < 6; ++i) mbar_init(smem_u32(&bars[i]), 1);   // a_free[4], b_full[2]
     mbar_init(bar_b_free, NI);                                       // every issuer commits per chunk
     mbar_init(bar_b_free + 8, NI);
     mbar_init(bar_acc, NI);                                          // every issuer commits per item
-    mbar_init(bar_a_full, STAGERS / 32);
-    mbar_init(bar_a_full + 8, STAGERS / 32);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_a_full + 8 * i, STAGERS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -241,9 +240,10 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
   const int n_items = items_per_nt * p.n_tiles;
 
   // role-private pipeline state
-  uint32_t a_fills0 = 0, a_fills1 = 0, b_loads0 = 0, b_loads1 = 0, b_count = 0;   // MMA lane
+  uint32_t b_loads0 = 0, b_loads1 = 0, b_count = 0;   // MMA lane
+  // activation ring of na (1, 2 or 4) buffers used round-robin: buffer = count & (na - 1), earlier uses = count >> na_log
+  const uint32_t na_mask = (uint32_t)na - 1u, na_log = (na == 4) ? 2u : (na == 2 ? 1u : 0u);
   int b_resident_nt = -1;
-  uint32_t a_uses0 = 0, a_uses1 = 0;                                              // stagers
   uint32_t a_count = 0, a_count_s = 0, acc_count = 0, item_count = 0;
   const uint32_t idesc_n = idesc_f16_m128(N), idesc_2n = idesc_f16_m128(2 * N);
   const uint32_t a_lo_delta = a_half >> 4;
@@ -325,14 +325,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
           if (load_b && !prefetched) issue_b_load(c, bb, bb ? b_loads1 : b_loads0);
           bool b_ready = !load_b;
           for (int g = 0; g < tiles; ++g) {
-            const int ab = (na == 2) ? (int)(a_count & 1) : 0;
+            const int ab = (int)(a_count & na_mask);
             if (g % NI != iw) {   // another issuer's tile: only keep the pipeline counters in step
-              if (ab) a_fills1 += 1; else a_fills0 += 1;
               a_count += 1;
               if (g == 0 && nb == 2 && c + 1 < p.n_chunks) { const int ob = bb ^ 1; issue_b_load(c + 1, ob, ob ? b_loads1 : b_loads0); }
               continue;
             }
-            mbar_wait(bar_a_full + 8 * ab, (ab ? a_fills1 : a_fills0) & 1);
+            mbar_wait(bar_a_full + 8 * ab, (a_count >> na_log) & 1);
             if (!b_ready) { mbar_wait(bar_b_full + 8 * bb, (bb ? b_loads1 : b_loads0) & 1); b_ready = true; }
             tc_fence_after();
             const uint64_t adesc0 = make_desc(A_addr + ab * a_bytes, (uint32_t)Rp * 16, 128);
@@ -354,7 +353,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
             }
             if (elect_one()) tc_commit(bar_a_free + 8 * ab);
             __syncwarp();
-            if (ab) a_fills1 += 1; else a_fills0 += 1;
             a_count += 1;
             if (g == 0 && nb == 2 && c + 1 < p.n_chunks) {
               // prefetch the next chunk's weights into the other buffer (loads counted when consumed)
@@ -380,8 +378,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
         const int c0 = c * KC;
         const bool fast = (a.Cin - c0) >= KC;
         for (int g = 0; g < tiles; ++g) {
-          const int ab = (na == 2) ? (int)(a_count_s & 1) : 0;
-          const uint32_t a_uses = ab ? a_uses1 : a_uses0;
+          const int ab = (int)(a_count_s & na_mask);
+          const uint32_t a_uses = a_count_s >> na_log;
           uint8_t* Ah = A0 + (size_t)ab * a_bytes;
           const int t_in0 = t_group0 + g * MT - a.pad_left;
           bool waited = (a_uses == 0);
@@ -444,7 +442,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_a_full + 8 * ab);
-          if (ab) a_uses1 += 1; else a_uses0 += 1;
           a_count_s += 1;
         }
       }
@@ -563,7 +560,11 @@ bool tc16_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
         const int KC = ((cin16 + nch - 1) / nch + 15) / 16 * 16;
         const int nb = (cin16 + KC - 1) / KC == 1 ? 1 : 2;
         if (tc16_conv_smem_bytes(K, dil, N, KC, MB, 2, nb) <= 216 * 1024) {
-          fill(1, N, n_tiles, KC, MB, 2, nb);
+          // a deeper activation ring hides the latency of the staging loads (the MMAs of a chunk are shorter than
+          // one round trip to L2); WETTS_TC16_ABUF=2 keeps the double buffer (experiments)
+          static const int max_na = getenv("WETTS_TC16_ABUF") ? atoi(getenv("WETTS_TC16_ABUF")) : 2;   // 4: opt-in until measured
+          const int na = (max_na >= 4 && nb == 2 && tc16_conv_smem_bytes(K, dil, N, KC, MB, 4, nb) <= 216 * 1024) ? 4 : 2;
+          fill(1, N, n_tiles, KC, MB, na, nb);
           return true;
         }
       }
