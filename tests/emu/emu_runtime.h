@@ -40,6 +40,11 @@ struct alignas(16) float4 {
 struct alignas(16) uint4 {
   uint32_t x, y, z, w;
 };
+struct alignas(8) float2 {
+  float x, y;
+};
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 #endif
 
 namespace emu {
@@ -212,6 +217,7 @@ WETTS_DEVICE long long clock_now() { return 0; }
 WETTS_DEVICE void spin_cycles(long long) {}
 WETTS_DEVICE void trap_now() { emu::die("kernel trap"); }
 WETTS_DEVICE int ldg_i32(const int* p) { return *p; }
+WETTS_DEVICE long long ldg_i64(const long long* p) { return *p; }
 WETTS_DEVICE float4 ldg4(const float* p) {
   if ((uintptr_t)p & 15) emu::die("16 B load from a misaligned address");
   return *reinterpret_cast<const float4*>(p);

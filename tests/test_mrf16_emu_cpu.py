@@ -87,3 +87,25 @@ def test_attention_tc_kernel_in_emulator(attn_emu_binary, case):
     """windowed relative-position attention (attentions.py:232-282) on the emulated tensor pipe vs an fp64 evaluation"""
     r = subprocess.run([attn_emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ---- pipelined per-layer conv kernel (tc16p_conv_kernel.cuh) in the same emulator
+@pytest.fixture(scope="module")
+def tc16p_emu_binary(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("emu_tc16p") / "tc16p_emu")
+    subprocess.run([gxx, "-O2", "-std=c++20", "-pthread", "-x", "c++", "-I", EMU, "-I", os.path.join(ROOT, "wetts_b200", "csrc"),
+                    os.path.join(EMU, "tc16p_emu.cpp"), "-o", out], check=True, capture_output=True, text=True)
+    return out
+
+
+# (Cin, Cout, K, dil, B, T, N, KC, grid, epilogue mode, length-aware): multi-chunk K loop, taps / dilation, several N tiles,
+# ragged T and masks, plain+relu / residual / gate epilogues, 2- and 4-slot activation rings, zero-tile items
+@pytest.mark.parametrize("case", [(48, 64, 5, 1, 2, 300, 64, 16, 2, 0, 0), (48, 64, 5, 1, 2, 300, 64, 16, 2, 1, 0),
+                                  (96, 128, 3, 2, 3, 520, 64, 32, 2, 2, 0), (40, 96, 7, 3, 2, 700, 32, 16, 3, 0, 1),
+                                  (192, 128, 1, 1, 2, 260, 128, 64, 1, 1, 0), (32, 64, 3, 12, 1, 1000, 64, 32, 1, 1, 1)])
+def test_pipelined_conv_kernel_in_emulator(tc16p_emu_binary, case):
+    r = subprocess.run([tc16p_emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -17,7 +17,7 @@ PY
 done
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2c_reference_arm.json 2> gpurun_out/r2c_reference_arm.err; echo "reference arm rc=$?"; head -c 600 gpurun_out/r2c_reference_arm.json
 # experiments (opt-in kernel variants): 4-deep activation ring of the per-layer kernel, C = 128 stage in the fused kernel
-for v in "WETTS_TC16_ABUF=4" "WETTS_MRF16_C128=1" "WETTS_TC16_ABUF=4 WETTS_MRF16_C128=1"; do
+for v in "WETTS_TC16_ABUF=4" "WETTS_MRF16_C128=1" "WETTS_TC16P=1" "WETTS_TC16P=1 WETTS_MRF16_C128=1"; do
   env $v timeout 300 python -m pytest tests/test_zz_widecases_gpu.py tests/test_mrf16_gpu.py tests/test_fused_gpu.py -q -x -m gpu > gpurun_out/r2c_exp_tests.log 2>&1; echo "[$v] tests rc=$? $(tail -1 gpurun_out/r2c_exp_tests.log)"
   env $v timeout 240 python bench.py --steps 5 --warmup 3 --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('[$v] ms/step', round(d['ms_per_step'],2), 'gen', round(d['roofline']['ms'],2))"
 done

@@ -3,88 +3,19 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "conv_args.h"
 #include "fused_mrf16_args.h"
 #include "fused_rb_args.h"
 
 namespace wetts {
 
-// ---------------------------------------------------------------- conv1d (fp32 SIMT)
-enum EpiMode : int {
-  EPI_PLAIN = 0,     // out = act(v + cond) [* mask]
-  EPI_RESID = 1,     // out = v + resid                         (ResBlock inner add)
-  EPI_MRF = 2,       // val = v + resid; acc_mode 0: out=val, 1: out+=val, 2: out=(out+val)/div
-  EPI_GATE = 3,      // paired channels -> tanh(a+ga)*sigmoid(b+gb)   (modules.py:76-77)
-  EPI_RES_SKIP = 4,  // co<H: x=(x+v)*mask ; co>=H: skip(+)=v         (modules.py:81-86)
-  EPI_COUPLING = 5,  // z1 = (z1 - v*mask)*mask                       (flows.py:510)
-  EPI_CONVT = 6,     // polyphase ConvTranspose1d scatter (tensor-core path only)
-};
-
-struct ConvEpilogue {
-  int mode = EPI_PLAIN;
-  float* out = nullptr;      // [B][*][T], batch stride out_bs, channel stride T
-  long long out_bs = 0;
-  const float* resid = nullptr;  // same geometry as out
-  const float* cond = nullptr;   // per (b, co) additive term, cond[b*cond_bs + cond_off + co]
-  int cond_bs = 0;
-  int cond_off = 0;
-  int act = 0;               // 0 none, 1 relu, 2 gelu (erf)
-  int out_mask = 0;          // multiply result by (t < lengths[b])
-  int acc_mode = 0;          // EPI_MRF
-  float div = 1.f;           // EPI_MRF final divisor
-  int H = 0;                 // EPI_GATE / EPI_RES_SKIP hidden size
-  float* x = nullptr;        // EPI_RES_SKIP residual stream (in place), batch stride out_bs
-  float* skip = nullptr;     // EPI_RES_SKIP skip accumulator, batch stride out_bs
-  int skip_init = 0;         // 1: skip = v (first layer), 0: skip += v
-  int last = 0;              // last WN layer: all Cout channels go to skip
-  int z_c0 = 0;              // EPI_COUPLING: target channel = z_c0 + co*z_cstep in `out`
-  int z_cstep = 1;
-  int up_u = 1, up_pad = 0;  // EPI_CONVT: stride and padding of the transposed conv
-  long long out_T = 0;       // EPI_CONVT: output samples per channel
-};
-
-// tiling of the tcgen05 implicit-GEMM path (tc_conv_kernel.cu), fixed per conv at load time
-struct TcPlan {
-  int mode = 0, N = 0, n_tiles = 0, KC = 0, n_chunks = 0, MB = 0, G = 0, n_abuf = 2, n_bbuf = 0, R_pad = 0, dil = 1;
-  int tmem_cols = 512;
-  size_t packed_floats = 0;
-};
-
-struct ConvArgs {
-  const float* wtc = nullptr;  // tensor-core packed weights, 3xTF32 layout (nullptr: not eligible)
-  TcPlan tc;
-  const void* wtc16 = nullptr; // tensor-core packed weights, f16-split layout (nullptr: not eligible)
-  TcPlan tc16;
-  int fmt = 32;               // operand format to use when both layouts exist: 16 = f16 split, 32 = 3xTF32
-  const float* in = nullptr;  // [B][Cin][T] view: element (b,ci,t) at in + b*in_bs + ci*in_cs + t
-  long long in_bs = 0;
-  int in_cs = 0;
-  const float* w = nullptr;   // packed [Cin][K][CoutPad]
-  const float* bias = nullptr;  // packed [CoutPad] or nullptr
-  int B = 0, Cin = 0, Cout = 0, CoutPad = 0, T = 0, K = 1, dil = 1, pad_left = 0;
-  int in_T = 0;               // valid input length when it differs from T (0: same as T); tensor-core path only
-  int pre_act = 0;            // 1: leaky_relu(pre_slope) applied to the input
-  float pre_slope = 0.1f;
-  const long long* lengths = nullptr;  // int64[B] or nullptr
-  int in_mask = 0;            // multiply the input by (t < lengths[b])
-  int use_tc = 1;             // 0: force the fp32 SIMT kernel for this call (per-handle / process option)
-  // length-aware mode (optional): work whose first output row lies at or beyond (la_len[b] + la_margin) * la_rate is
-  // skipped (la_len in frames of z, la_rate = rows of THIS conv's time axis per frame); the skipped output rows are
-  // left unwritten
-  const long long* la_len = nullptr;
-  int la_rate = 1, la_margin = 0;
-  ConvEpilogue ep;
-};
+// ---------------------------------------------------------------- conv1d (argument structs: conv_args.h)
 void launch_conv1d(const ConvArgs& a, cudaStream_t s);
 // out[b][co] = bias[co] + sum_ci w[ci][co] g[b][ci]   (w: SIMT layout of a 1x1 conv, [Cin][1][CoutPad])
 void launch_cond_vector(const float* g, const float* w, const float* bias, float* out, int B, int Cin, int Cout,
                         int CoutPad, cudaStream_t s);
 void launch_conv1d_simt(const ConvArgs& a, cudaStream_t s);
 
-struct TcConvArgs {
-  ConvArgs c;
-  const float* wtc;
-  int N, n_tiles, KC, n_chunks, MB, G, n_abuf, n_bbuf, R_pad, tmem_cols;
-};
 // Probes (once) the shared-window offset at which dynamic shared memory starts for kernels without static
 // shared memory.  tcgen05 descriptors built from this kernel parameter are uniform by construction.
 int dyn_smem_offset(uint32_t* off, cudaStream_t s);
@@ -99,6 +30,11 @@ size_t tc16_conv_smem_bytes(int K, int dil, int N, int KC, int MB, int n_abuf, i
 void launch_pack_conv_tc16(const float* src, void* dst, const int* co_map, const int* ci_map, int Cout, int Cin, int K,
                            int src_cin, const TcPlan& pl, cudaStream_t s);
 void launch_conv1d_tc16(const ConvArgs& a, cudaStream_t s);
+// pipelined variant (tc16p_conv.cu): same weights and plan, dedicated staging / epilogue warps; false = not taken
+bool launch_conv1d_tc16p(const ConvArgs& a, cudaStream_t s);
+bool tc16p_enabled();
+void set_tc16p_enabled(bool on);
+int tc16p_install_fault_word(unsigned int* word);
 void set_tensor_cores_enabled(bool on);
 bool tensor_cores_enabled();
 

@@ -1,0 +1,52 @@
+// Launch side of the pipelined per-layer f16 conv kernel (tc16p_conv_kernel.cuh).  It consumes the packed weights and
+// the tiling plan of tc16_conv_kernel.cu unchanged.
+#include <atomic>
+#include <cstdlib>
+
+#include "kernels.cuh"
+#include "tc16p_conv_kernel.cuh"
+
+namespace wetts {
+
+static std::atomic<int> g_tc16p{-1};
+bool tc16p_enabled() {
+  int v = g_tc16p.load();
+  if (v < 0) {
+    v = getenv("WETTS_TC16P") ? (atoi(getenv("WETTS_TC16P")) != 0) : 0;   // opt-in until measured on hardware
+    g_tc16p.store(v);
+  }
+  return v != 0;
+}
+void set_tc16p_enabled(bool on) { g_tc16p.store(on ? 1 : 0); }
+
+// true if the launch was taken (large-mode plan whose ring fits); false: the caller uses conv1d_tc16_kernel
+bool launch_conv1d_tc16p(const ConvArgs& a, cudaStream_t s) {
+  const TcPlan& pl = a.tc16;
+  if (pl.mode != 1) return false;
+  const int MB = (a.T > 128 && pl.MB == 2) ? 2 : 1;
+  int na = kTc16pNA;
+  if (tc16p_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, na) > 227 * 1024) na = 2;
+  const size_t smem = tc16p_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, na);
+  if (smem > 227 * 1024) return false;
+  TcConvArgs p;
+  p.c = a;
+  p.wtc = reinterpret_cast<const float*>(a.wtc16);
+  const int R = 128 * MB + (a.K - 1) * a.dil;
+  p.N = pl.N; p.n_tiles = pl.n_tiles; p.KC = pl.KC; p.n_chunks = pl.n_chunks; p.MB = MB;
+  p.tmem_cols = pl.tmem_cols; p.G = pl.tmem_cols / (MB * 2 * pl.N);
+  p.n_abuf = na; p.n_bbuf = 2; p.R_pad = (R + 7) & ~7;
+  static DynSmemAttr attr;
+  if (attr.ensure((const void*)conv1d_tc16p_kernel, smem) != cudaSuccess) return true;   // error recorded; nothing launched
+  const int n_sm = current_device_sm_count();
+  if (n_sm <= 0) return true;
+  const int group_rows = p.G * 128 * MB;
+  const long long items = (long long)a.B * ((a.T + group_rows - 1) / group_rows) * pl.n_tiles;
+  const int grid = (int)(items < n_sm ? items : n_sm);
+  conv1d_tc16p_kernel<<<grid, kTc16pThreads, smem, s>>>(p);
+  count_launch();
+  return true;
+}
+
+int tc16p_install_fault_word(unsigned int* word) { return tc::install_fault_word_tu(word) == cudaSuccess ? 0 : 1; }
+
+}  // namespace wetts

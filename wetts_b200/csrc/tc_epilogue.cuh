@@ -1,0 +1,146 @@
+// Fused conv epilogues of the tensor-pipe kernels in host-compilable form (no CUDA dependency beyond the tc_prims.cuh
+// wrappers): the same code runs on the device and in the host CTA emulator.  Semantics: EpiMode in conv_args.h.
+#pragma once
+#include <math.h>
+
+#include "conv_args.h"
+#include "tc_prims.cuh"
+
+namespace wetts {
+
+WETTS_DEVICE float ep_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+WETTS_DEVICE float ep_gelu(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+WETTS_DEVICE int ep_min(int a, int b) { return a < b ? a : b; }
+
+// Fused epilogue of one 16-channel slice of one output row, specialised per mode with the switch
+// hoisted out of the element loops: all global loads of the slice are issued before the first store.
+// v[i] already contains bias (+ conditioning).
+WETTS_DEVICE void tc_epilogue_slice_p(const ConvArgs& a, int b, int t, int co0, float* v, float msk) {
+  const ConvEpilogue& e = a.ep;
+  const size_t Ts = (size_t)a.T;
+  const size_t row = (size_t)b * (size_t)e.out_bs + (size_t)t;
+  const int nval = ep_min(16, a.Cout - co0);
+  switch (e.mode) {
+    case EPI_PLAIN: {
+      float* op = e.out + row + (size_t)co0 * Ts;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = v[i];
+        if (e.act == 1) x = fmaxf(x, 0.f);
+        else if (e.act == 2) x = ep_gelu(x);
+        if (e.out_mask) x *= msk;
+        if (i < nval) op[(size_t)i * Ts] = x;
+      }
+      break;
+    }
+    case EPI_RESID: {
+      const float* rp = e.resid + row + (size_t)co0 * Ts;
+      float* op = e.out + row + (size_t)co0 * Ts;
+      float r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? rp[(size_t)i * Ts] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nval) op[(size_t)i * Ts] = v[i] + r[i];
+      break;
+    }
+    case EPI_MRF: {
+      const float* rp = e.resid + row + (size_t)co0 * Ts;
+      float* op = e.out + row + (size_t)co0 * Ts;
+      float r[16], o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? rp[(size_t)i * Ts] : 0.f;
+      if (e.acc_mode != 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = (i < nval) ? op[(size_t)i * Ts] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = v[i] + r[i];
+        if (e.acc_mode == 1) x = o[i] + x;
+        else if (e.acc_mode == 2) x = (o[i] + x) / e.div;
+        if (i < nval) op[(size_t)i * Ts] = x;
+      }
+      break;
+    }
+    case EPI_GATE: {
+      float* op = e.out + row + (size_t)(co0 >> 1) * Ts;
+#pragma unroll
+      for (int i = 0; i < 16; i += 2)
+        if (i < nval) op[(size_t)(i >> 1) * Ts] = tanhf(v[i]) * ep_sigmoid(v[i + 1]);
+      break;
+    }
+    case EPI_RES_SKIP: {
+      if (!e.last && co0 < e.H) {  // residual stream (a 16-slice never straddles H: H % 16 == 0 is checked on the host)
+        float* xp = e.x + row + (size_t)co0 * Ts;
+        float r[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? xp[(size_t)i * Ts] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nval) xp[(size_t)i * Ts] = (r[i] + v[i]) * msk;
+      } else {
+        float* sp = e.skip + row + (size_t)(e.last ? co0 : co0 - e.H) * Ts;
+        float r[16];
+        if (!e.skip_init) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? sp[(size_t)i * Ts] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nval) sp[(size_t)i * Ts] = e.skip_init ? v[i] : r[i] + v[i];
+      }
+      break;
+    }
+    case EPI_CONVT: {
+      // polyphase ConvTranspose1d: packed channel = co*u + r, row t = input frame q; output sample
+      // n = q*u + r - pad of channel co.  The u phases of one (q, co) are u consecutive samples, so a slice of
+      // 16 packed channels is 16/u runs of u contiguous floats: written with 8 / 16 B stores when the run is
+      // inside the signal and suitably aligned (u = 4: pad 2 -> 8 B; u = 8: pad 4 -> 16 B), else sample by sample.
+      const int u = e.up_u;
+      const long long n0 = (long long)t * u - e.up_pad;
+      float* ob = e.out + (size_t)b * (size_t)e.out_bs;
+      const bool whole = (nval == 16) && (n0 >= 0) && (n0 + u <= e.out_T) && ((e.out_T & 3) == 0);
+      if (u == 8 && whole && (co0 & 7) == 0 && (n0 & 3) == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          float4* dst = reinterpret_cast<float4*>(ob + (size_t)((co0 + i) >> 3) * (size_t)e.out_T + (size_t)n0);
+          dst[0] = make_float4(v[i + 0], v[i + 1], v[i + 2], v[i + 3]);
+          dst[1] = make_float4(v[i + 4], v[i + 5], v[i + 6], v[i + 7]);
+        }
+      } else if (u == 4 && whole && (co0 & 3) == 0 && (n0 & 1) == 0) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          float2* dst = reinterpret_cast<float2*>(ob + (size_t)((co0 + i) >> 2) * (size_t)e.out_T + (size_t)n0);
+          dst[0] = make_float2(v[i + 0], v[i + 1]);
+          dst[1] = make_float2(v[i + 2], v[i + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int cp = co0 + i;
+          const int co = cp / u, r = cp - co * u;
+          const long long n = n0 + r;
+          if (i < nval && n >= 0 && n < e.out_T) ob[(size_t)co * (size_t)e.out_T + (size_t)n] = v[i];
+        }
+      }
+      break;
+    }
+    case EPI_COUPLING: {
+      float* zp = e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts;
+      const long long step = (long long)e.z_cstep * (long long)Ts;
+      float r[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? zp[(long long)i * step] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nval) zp[(long long)i * step] = (r[i] - v[i] * msk) * msk;
+      break;
+    }
+    default:
+      break;
+  }
+}
+
+
+}  // namespace wetts

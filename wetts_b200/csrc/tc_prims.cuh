@@ -38,6 +38,7 @@ WETTS_DEVICE void spin_cycles(long long n) {     // busy-wait n SM cycles (start
 WETTS_DEVICE void trap_now() { __trap(); }
 WETTS_DEVICE float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 WETTS_DEVICE int ldg_i32(const int* p) { return __ldg(p); }
+WETTS_DEVICE long long ldg_i64(const long long* p) { return __ldg(p); }
 
 WETTS_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
