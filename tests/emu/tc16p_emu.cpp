@@ -58,11 +58,14 @@ int main(int argc, char** argv) {
   if (la) { a.la_len = la_len.data(); a.la_rate = 1; a.la_margin = 3; }
   p.wtc = reinterpret_cast<const float*>(packed);
   const int R = 128 * MB + (K - 1) * dil;
-  int na = kTc16pNA;
-  if (tc16p_smem_bytes(K, dil, N, KC, MB, na) > emu::kSmemBytes) na = 2;
-  p.N = N; p.n_tiles = n_tiles; p.KC = KC; p.n_chunks = n_chunks; p.MB = MB; p.G = G; p.n_abuf = na; p.n_bbuf = 2;
+  int na = 2, nbuf = 2;     // same policy as launch_conv1d_tc16p: weight slots first, then activation slots
+  const int nb_max = getenv("EMU_NB") ? atoi(getenv("EMU_NB")) : kTc16pNB;
+  while (nbuf < nb_max && tc16p_smem_bytes(K, dil, N, KC, MB, na, nbuf + 1) <= emu::kSmemBytes) ++nbuf;
+  if (tc16p_smem_bytes(K, dil, N, KC, MB, 4, nbuf) <= emu::kSmemBytes) na = 4;
+  p.N = N; p.n_tiles = n_tiles; p.KC = KC; p.n_chunks = n_chunks; p.MB = MB; p.G = G; p.n_abuf = na; p.n_bbuf = nbuf;
   p.R_pad = (R + 7) & ~7; p.tmem_cols = tmem_cols;
-  if (tc16p_smem_bytes(K, dil, N, KC, MB, na) > emu::kSmemBytes) { printf("smem over budget\n"); return 64; }
+  if (tc16p_smem_bytes(K, dil, N, KC, MB, na, nbuf) > emu::kSmemBytes) { printf("smem over budget\n"); return 64; }
+  printf("rings: %d activation slots, %d weight slots\n", na, nbuf);
   unsigned long long n_mma = 0;
   emu::launch(conv1d_tc16p_kernel, p, grid, kTc16pThreads, &n_mma);
   // reference

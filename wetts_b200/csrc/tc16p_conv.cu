@@ -24,17 +24,21 @@ bool launch_conv1d_tc16p(const ConvArgs& a, cudaStream_t s) {
   const TcPlan& pl = a.tc16;
   if (pl.mode != 1) return false;
   const int MB = (a.T > 128 && pl.MB == 2) ? 2 : 1;
-  int na = kTc16pNA;
-  if (tc16p_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, na) > 227 * 1024) na = 2;
-  const size_t smem = tc16p_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, na);
-  if (smem > 227 * 1024) return false;
+  // ring depths: weight slots first (up to 4; what the MMAs wait for), then activation slots (4 or 2)
+  static const int max_nb = getenv("WETTS_TC16P_NB") ? atoi(getenv("WETTS_TC16P_NB")) : kTc16pNB;
+  const size_t cap = 227 * 1024;
+  int nb = 2, na = 2;
+  if (tc16p_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, na, nb) > cap) return false;
+  while (nb < max_nb && nb < kTc16pNB && tc16p_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, na, nb + 1) <= cap) ++nb;
+  if (tc16p_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, 4, nb) <= cap) na = 4;
+  const size_t smem = tc16p_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, na, nb);
   TcConvArgs p;
   p.c = a;
   p.wtc = reinterpret_cast<const float*>(a.wtc16);
   const int R = 128 * MB + (a.K - 1) * a.dil;
   p.N = pl.N; p.n_tiles = pl.n_tiles; p.KC = pl.KC; p.n_chunks = pl.n_chunks; p.MB = MB;
   p.tmem_cols = pl.tmem_cols; p.G = pl.tmem_cols / (MB * 2 * pl.N);
-  p.n_abuf = na; p.n_bbuf = 2; p.R_pad = (R + 7) & ~7;
+  p.n_abuf = na; p.n_bbuf = nb; p.R_pad = (R + 7) & ~7;
   static DynSmemAttr attr;
   if (attr.ensure((const void*)conv1d_tc16p_kernel, smem) != cudaSuccess) return true;   // error recorded; nothing launched
   const int n_sm = current_device_sm_count();

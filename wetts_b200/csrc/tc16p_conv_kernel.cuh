@@ -7,7 +7,7 @@
 //
 //   warp 0          MMA issuer      wait acc_empty, then per chunk: wait b_full, per tile: wait a_full -> MMAs -> commit
 //                                    a_free; commit b_free; at the end of the item commit acc_full
-//   warp 1          weight producer  per chunk: wait b_free (2-slot ring) -> cp.async.bulk -> b_full
+//   warp 1          weight producer  per chunk: wait b_free (NB-slot ring, 2..4) -> cp.async.bulk -> b_full
 //   warps 2 .. 7    stagers          per (chunk, tile): wait a_free (NA-slot ring) -> global loads, lrelu / masks / zero
 //                                    padding, fp32 -> f16 split -> a_full
 //   warps 8 .. 15   epilogue         wait acc_full -> TMEM -> fused epilogue (tc_epilogue.cuh) -> acc_empty
@@ -29,11 +29,14 @@ constexpr int kTc16pThreads = 512;
 constexpr int kTc16pNA = 4;            // activation ring slots (maximum; 2 when 4 do not fit in shared memory)
 constexpr int kTc16pStagerWarp0 = 2, kTc16pStagers = 6 * 32, kTc16pEpiWarp0 = 8, kTc16pEpiWarps = 8;
 
-// shared memory: [bars 128 B][A ring: NA x (hi | lo')][B ring: 2 x weight tile]
-inline size_t tc16p_smem_bytes(int K, int dil, int N, int KC, int MB, int na = kTc16pNA) {
+constexpr int kTc16pNB = 4;            // weight ring slots (maximum)
+// shared memory: [bars 192 B][A ring: NA x (hi | lo')][B ring: NB x weight tile].  The weight stream is what the MMAs
+// wait for (a 41 KB chunk of a flow in_layer feeds 1.9 k cycles of MMAs, less than one bulk-copy round trip to L2), so
+// the launcher deepens the weight ring first and the activation ring with what is left.
+inline size_t tc16p_smem_bytes(int K, int dil, int N, int KC, int MB, int na = kTc16pNA, int nb = 2) {
   const int R = 128 * MB + (K - 1) * dil;
   const int Rp = (R + 7) & ~7;
-  return 128 + (size_t)na * (2 * (size_t)(KC / 8) * Rp * 16) + 2 * ((size_t)K * (KC / 8) * 2 * N * 16);
+  return 192 + (size_t)na * (2 * (size_t)(KC / 8) * Rp * 16) + (size_t)nb * ((size_t)K * (KC / 8) * 2 * N * 16);
 }
 
 WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(const TcConvArgs p) {
@@ -52,17 +55,18 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
   const uint32_t b_bytes = (uint32_t)K * (KC / 8) * 2 * N * 16;
   const uint32_t tmem_cols = (uint32_t)p.tmem_cols;
   const uint32_t NA = (uint32_t)p.n_abuf, na_log = (p.n_abuf == 4) ? 2u : 1u;      // ring of 2 or 4 slots
+  const uint32_t NB = (uint32_t)p.n_bbuf;                                           // 2, 3 or 4 slots
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 120);
-  uint8_t* A0 = smem + 128;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 184);
+  uint8_t* A0 = smem + 192;
   uint8_t* B0 = A0 + (size_t)NA * a_bytes;
   const uint32_t bar_a_free = smem_u32(&bars[0]);    // [NA] MMA -> stagers
   const uint32_t bar_a_full = smem_u32(&bars[4]);    // [NA] stagers -> MMA
-  const uint32_t bar_b_full = smem_u32(&bars[8]);    // [2]  bulk copy -> MMA
-  const uint32_t bar_b_free = smem_u32(&bars[10]);   // [2]  MMA -> producer
-  const uint32_t bar_acc_full = smem_u32(&bars[12]); //      MMA -> epilogue warps
-  const uint32_t bar_acc_empty = smem_u32(&bars[13]);//      epilogue warps -> MMA
+  const uint32_t bar_b_full = smem_u32(&bars[8]);    // [4]  bulk copy -> MMA
+  const uint32_t bar_b_free = smem_u32(&bars[12]);   // [4]  MMA -> producer
+  const uint32_t bar_acc_full = smem_u32(&bars[16]); //      MMA -> epilogue warps
+  const uint32_t bar_acc_empty = smem_u32(&bars[17]);//      epilogue warps -> MMA
   const uint32_t A_addr = smem_u32(A0), B_addr = smem_u32(B0);
 
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), tmem_cols);
@@ -71,7 +75,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
       mbar_init(bar_a_free + 8 * i, 1);
       mbar_init(bar_a_full + 8 * i, kTc16pStagers / 32);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kTc16pNB; ++i) {
       mbar_init(bar_b_full + 8 * i, 1);
       mbar_init(bar_b_free + 8 * i, 1);
     }
@@ -107,15 +111,14 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
     // =============================== MMA issuer ===============================
     const uint32_t idesc_n = idesc_f16_m128(N), idesc_2n = idesc_f16_m128(2 * N);
     const uint32_t a_lo_delta = a_half >> 4;
-    uint32_t a_cnt = 0, b_cnt = 0, it_cnt = 0;
+    uint32_t a_cnt = 0, bb = 0, b_use = 0, it_cnt = 0;   // weight ring position: slot bb, earlier uses of it b_use
     for (int item = WETTS_BID; item < n_items; item += WETTS_NBLK) {
       int nt, b, t_group0, tiles, nch;
       decode(item, nt, b, t_group0, tiles, nch);
       if (it_cnt > 0) mbar_wait(bar_acc_empty, (it_cnt - 1) & 1);      // the previous item's accumulators are drained
       tc_fence_after();
       for (int c = 0; c < nch; ++c) {
-        const uint32_t bb = b_cnt & 1u;
-        mbar_wait(bar_b_full + 8 * bb, (b_cnt >> 1) & 1);
+        mbar_wait(bar_b_full + 8 * bb, b_use & 1);
         for (int g = 0; g < tiles; ++g) {
           const uint32_t ab = a_cnt & (NA - 1u);
           mbar_wait(bar_a_full + 8 * ab, (a_cnt >> na_log) & 1);
@@ -143,7 +146,8 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
         }
         if (elect_one()) tc_commit(bar_b_free + 8 * bb);
         warp_sync();
-        b_cnt += 1;
+        bb += 1;
+        if (bb == NB) { bb = 0; b_use += 1; }
       }
       if (elect_one()) tc_commit(bar_acc_full);
       warp_sync();
@@ -151,12 +155,11 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
     }
   } else if (warp == 1) {
     // =============================== weight producer ===============================
-    uint32_t b_cnt = 0;
+    uint32_t bb = 0, use = 0;
     for (int item = WETTS_BID; item < n_items; item += WETTS_NBLK) {
       int nt, b, t_group0, tiles, nch;
       decode(item, nt, b, t_group0, tiles, nch);
       for (int c = 0; c < nch; ++c) {
-        const uint32_t bb = b_cnt & 1u, use = b_cnt >> 1;
         if (use > 0) mbar_wait(bar_b_free + 8 * bb, (use - 1) & 1);
         warp_sync();
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + c) * b_bytes;
@@ -169,7 +172,8 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
           }
         }
         warp_sync();
-        b_cnt += 1;
+        bb += 1;
+        if (bb == NB) { bb = 0; use += 1; }
       }
     }
   } else if (warp < kTc16pEpiWarp0) {
