@@ -75,6 +75,9 @@ struct TcConvArgs {
   ConvArgs c;
   const float* wtc;
   int N, n_tiles, KC, n_chunks, MB, G, n_abuf, n_bbuf, R_pad, tmem_cols;
+  int nt_minor = 0;     // work items ordered (rows, N tile) instead of (N tile, rows): the tiles of one row block run side by side
+  int debug_skip = 0;   // experiments only (WETTS_TC16_DEBUG_SKIP): 1 = no staging work, 2 = no epilogue work (wrong results)
+  int l2_prefetch = 0;  // warm L2 one work item ahead (activations) and for this item's epilogue operands
 };
 
 }  // namespace wetts

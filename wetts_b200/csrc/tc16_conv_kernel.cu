@@ -239,6 +239,22 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
   const int items_per_nt = a.B * n_groups;
   const int n_items = items_per_nt * p.n_tiles;
 
+  // item -> (N tile, utterance, first row).  Layers whose weights stream per item anyway (several chunks) run the N tiles
+  // of one row block in consecutive items, i.e. on neighbouring CTAs at the same time: the tiles read the same activation
+  // rows, which then come from DRAM once (ncu, in_layer of the flow: 443 MB read for a 126 MB tensor in N-tile-major order).
+  auto decode_item = [&](int it, int& nt_, int& b_, int& t0_) {
+    int rem;
+    if (p.nt_minor) {
+      rem = it / p.n_tiles;
+      nt_ = it - rem * p.n_tiles;
+    } else {
+      nt_ = it / items_per_nt;
+      rem = it - nt_ * items_per_nt;
+    }
+    b_ = rem / n_groups;
+    t0_ = (rem - b_ * n_groups) * group_rows;
+  };
+
   // role-private pipeline state
   uint32_t b_loads0 = 0, b_loads1 = 0, b_count = 0;   // MMA lane
   // activation ring of na (1, 2 or 4) buffers used round-robin: buffer = count & (na - 1), earlier uses = count >> na_log
@@ -250,10 +266,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
   const int nb16 = KC / 16;                 // KC is a multiple of 16 (one tcgen05.mma k-step)
 
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int nt = item / items_per_nt;
-    const int rem = item - nt * items_per_nt;
-    const int b = rem / n_groups;
-    const int t_group0 = (rem - b * n_groups) * group_rows;
+    int nt, b, t_group0;
+    decode_item(item, nt, b, t_group0);
     // length-aware mode: a group wholly beyond (len + margin) frames runs with zero tiles (no staging, no MMAs, empty
     // epilogue; the per-item barriers still tick).  A select, not a branch (SASS-checked: a `continue` here, or votes
     // on the tile count, cost the issue loop its uniform datapath: R2UR 19 -> 162).
@@ -374,6 +388,35 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
       const int Tin = a.in_T > 0 ? a.in_T : T;
       const int t_hi = a.in_mask ? (int)(len < Tin ? len : Tin) : Tin;
       const float* in_b = a.in + (long long)b * a.in_bs;
+      if (p.l2_prefetch) {
+        // (1) the activation rows of this CTA's NEXT item: its staging loads (16 per thread and round, one round trip per
+        // chunk on the critical path of the MMAs) then hit L2; (2) what this item's epilogue reads back.
+        const int nxt = item + (int)gridDim.x;
+        if (nxt < n_items) {
+          int nt_n, b_n, t0_n;
+          decode_item(nxt, nt_n, b_n, t0_n);
+          const long long len_n = a.lengths ? a.lengths[b_n] : (long long)T;
+          const int t_hi_n = a.in_mask ? (int)(len_n < Tin ? len_n : Tin) : Tin;
+          const int lo = max(0, t0_n - a.pad_left), hi = min(t_hi_n, t0_n - a.pad_left + G * MT + (K - 1) * dil);
+          l2_prefetch_rows(a.in + (long long)b_n * a.in_bs, a.in_cs, a.Cin, lo, hi, tid, STAGERS);
+        }
+        const ConvEpilogue& e = a.ep;
+        const int c_lo = nt * N, c_hi = min(a.Cout, nt * N + N);
+        const int r_lo = t_group0, r_hi = min(T, t_group0 + tiles * MT);
+        const long long ob = (long long)b * e.out_bs;
+        if (e.mode == EPI_RESID || e.mode == EPI_MRF) {
+          l2_prefetch_rows(e.resid + ob + (long long)c_lo * T, T, c_hi - c_lo, r_lo, r_hi, tid, STAGERS);
+          if (e.mode == EPI_MRF && e.acc_mode != 0) l2_prefetch_rows(e.out + ob + (long long)c_lo * T, T, c_hi - c_lo, r_lo, r_hi, tid, STAGERS);
+        } else if (e.mode == EPI_RES_SKIP) {
+          if (!e.last && c_lo < e.H) l2_prefetch_rows(e.x + ob + (long long)c_lo * T, T, min(c_hi, e.H) - c_lo, r_lo, r_hi, tid, STAGERS);
+          if (!e.skip_init && (e.last || c_hi > e.H)) {
+            const int s_lo = e.last ? c_lo : max(c_lo, e.H) - e.H, s_hi = e.last ? c_hi : c_hi - e.H;
+            l2_prefetch_rows(e.skip + ob + (long long)s_lo * T, T, s_hi - s_lo, r_lo, r_hi, tid, STAGERS);
+          }
+        } else if (e.mode == EPI_COUPLING) {
+          l2_prefetch_rows(e.out + ob + (long long)(e.z_c0 + c_lo * e.z_cstep) * T, (long long)e.z_cstep * T, c_hi - c_lo, r_lo, r_hi, tid, STAGERS);
+        }
+      }
       for (int c = 0; c < n_chunks_item; ++c) {
         const int c0 = c * KC;
         const bool fast = (a.Cin - c0) >= KC;
@@ -386,6 +429,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
           // two (row, 16-channel) items per round: 32 independent global loads per thread in flight
           int q16 = 0, r = tid;
           while (r >= Rp) { r -= Rp; ++q16; }
+          if (p.debug_skip & 1) q16 = nb16;
           while (q16 < nb16) {
             int q16b = q16, rb = r + STAGERS;
             while (rb >= Rp) { rb -= Rp; ++q16b; }
@@ -454,7 +498,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
       constexpr int COLSPLIT = THREADS / 128;     // warps sharing a TMEM lane quarter split the columns
       const int q = warp & 3, part = warp >> 2;
       const int ncol = N / COLSPLIT;
-      for (int g = 0; g < tiles; ++g) {
+      const int tiles_e = (p.debug_skip & 2) ? 0 : tiles;
+      for (int g = 0; g < tiles_e; ++g) {
         for (int mb = 0; mb < MB; ++mb) {
           const int t = t_group0 + g * MT + mb * 128 + q * 32 + lane;
           const float msk = (t < len) ? 1.f : 0.f;
@@ -595,6 +640,12 @@ void launch_conv1d_tc16(const ConvArgs& a, cudaStream_t s) {
   p.tmem_cols = pl.tmem_cols; p.G = pl.tmem_cols / (MB * 2 * pl.N);
   p.n_abuf = pl.n_abuf; p.n_bbuf = pl.n_bbuf; p.R_pad = (R + 7) & ~7;
   const size_t smem = tc16_conv_smem_bytes(a.K, a.dil, pl.N, pl.KC, MB, pl.n_abuf, pl.n_bbuf);
+  static const int opt_nt_minor = getenv("WETTS_TC16_NTMINOR") ? atoi(getenv("WETTS_TC16_NTMINOR")) : 1;
+  static const int opt_prefetch = getenv("WETTS_TC16_PREFETCH") ? atoi(getenv("WETTS_TC16_PREFETCH")) : 1;
+  p.nt_minor = (opt_nt_minor && pl.n_chunks > 1 && pl.n_tiles > 1) ? 1 : 0;
+  p.l2_prefetch = opt_prefetch;
+  static const int opt_skip = getenv("WETTS_TC16_DEBUG_SKIP") ? atoi(getenv("WETTS_TC16_DEBUG_SKIP")) : 0;
+  p.debug_skip = opt_skip;
   static DynSmemAttr attr[2];
   const int n_sm = current_device_sm_count();
   if (n_sm <= 0) return;

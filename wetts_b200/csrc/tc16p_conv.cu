@@ -38,7 +38,9 @@ bool launch_conv1d_tc16p(const ConvArgs& a, cudaStream_t s) {
   const int R = 128 * MB + (a.K - 1) * a.dil;
   p.N = pl.N; p.n_tiles = pl.n_tiles; p.KC = pl.KC; p.n_chunks = pl.n_chunks; p.MB = MB;
   p.tmem_cols = pl.tmem_cols; p.G = pl.tmem_cols / (MB * 2 * pl.N);
-  p.n_abuf = na; p.n_bbuf = nb; p.R_pad = (R + 7) & ~7;
+  p.n_abuf = na; p.n_bbuf = nb;
+  static const int opt_skip = getenv("WETTS_TC16_DEBUG_SKIP") ? atoi(getenv("WETTS_TC16_DEBUG_SKIP")) : 0;
+  p.debug_skip = opt_skip; p.R_pad = (R + 7) & ~7;
   static DynSmemAttr attr;
   if (attr.ensure((const void*)conv1d_tc16p_kernel, smem) != cudaSuccess) return true;   // error recorded; nothing launched
   const int n_sm = current_device_sm_count();

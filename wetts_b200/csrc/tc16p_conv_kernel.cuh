@@ -196,7 +196,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
           const int t_in0 = t_group0 + g * MT - a.pad_left;
           bool waited = (use == 0);
           // one (row, 16-channel) unit per round: 16 independent loads in flight per thread
-          for (int u = st; u < nb16 * Rp; u += kTc16pStagers) {
+          for (int u = (p.debug_skip & 1) ? nb16 * Rp : st; u < nb16 * Rp; u += kTc16pStagers) {
             const int q16 = u / Rp, r = u - q16 * Rp;
             const int t = t_in0 + r;
             const bool rok = (r < R) && (t >= 0) && (t < t_hi);
@@ -246,7 +246,8 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
       const long long len = a.lengths ? ldg_i64(a.lengths + b) : (long long)T;
       mbar_wait(bar_acc_full, it_cnt & 1);
       tc_fence_after();
-      for (int g = 0; g < tiles; ++g) {
+      const int tiles_e = (p.debug_skip & 2) ? 0 : tiles;
+      for (int g = 0; g < tiles_e; ++g) {
         for (int mb = 0; mb < MB; ++mb) {
           const int t = t_group0 + g * MT + mb * 128 + q * 32 + lane;
           const float msk = (t < len) ? 1.f : 0.f;
