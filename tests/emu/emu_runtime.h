@@ -202,6 +202,12 @@ inline void flush_for(uint32_t bar) {
   }
 }
 
+// seconds one mbarrier wait may take before it is reported as a deadlock (EMU_TIMEOUT_S; emulated MMAs are slow, and a
+// role that waits for a whole work item of another role can legitimately wait long on a loaded machine)
+inline int wait_timeout_s() {
+  static const int v = getenv("EMU_TIMEOUT_S") ? atoi(getenv("EMU_TIMEOUT_S")) : 20;
+  return v;
+}
 }  // namespace emu
 
 namespace wetts {
@@ -245,7 +251,7 @@ WETTS_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
     }
     if (++spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(50));
     else std::this_thread::yield();
-    if ((spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+    if ((spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(emu::wait_timeout_s())) {
       fprintf(stderr, "mbarrier 0x%x parity %u\n", bar, parity);
       emu::die("mbarrier wait timed out (deadlock)");
     }

@@ -95,7 +95,7 @@ __device__ __forceinline__ void tc16_epilogue_slice(const ConvArgs& a, int b, in
       float* op = e.out + row + (size_t)(co0 >> 1) * Ts;
 #pragma unroll
       for (int i = 0; i < 16; i += 2)
-        if (i < nval) op[(size_t)(i >> 1) * Ts] = tanhf(v[i]) * sigmoidf_acc(v[i + 1]);
+        if (i < nval) op[(size_t)(i >> 1) * Ts] = gate_tanh_sigmoid_fast(v[i], v[i + 1]);
       break;
     }
     case EPI_RES_SKIP: {
@@ -595,10 +595,13 @@ bool tc16_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
       }
   }
   // ---- large mode (N a multiple of 64 so that 16 warps split the columns in 16-wide pieces)
+  // WETTS_TC16_NMAX=64 (read once, at load time): 64-wide N tiles, so that two items' accumulators fit in TMEM and the
+  // pipelined kernel can drain one while the MMAs of the next run
+  static const int n_max = getenv("WETTS_TC16_NMAX") ? atoi(getenv("WETTS_TC16_NMAX")) : 128;
   const int cout64 = (Cout + 63) / 64 * 64;
-  for (int n_tiles = (cout64 + 127) / 128; n_tiles <= cout64 / 64; ++n_tiles) {
+  for (int n_tiles = (cout64 + n_max - 1) / n_max; n_tiles <= cout64 / 64; ++n_tiles) {
     const int N = ((cout64 + n_tiles - 1) / n_tiles + 63) / 64 * 64;
-    if (N > 128) continue;
+    if (N > n_max) continue;
     for (int MB = 2; MB >= 1; --MB) {
       if (MB * 2 * N > 512) continue;
       for (int nch = 1; nch <= cin16 / 16; ++nch) {

@@ -37,8 +37,17 @@ bool launch_conv1d_tc16p(const ConvArgs& a, cudaStream_t s) {
   p.wtc = reinterpret_cast<const float*>(a.wtc16);
   const int R = 128 * MB + (a.K - 1) * a.dil;
   p.N = pl.N; p.n_tiles = pl.n_tiles; p.KC = pl.KC; p.n_chunks = pl.n_chunks; p.MB = MB;
+  // two accumulator sets when one item (two M blocks) needs at most half of TMEM: ping-pong between MMAs and drain
+  static const int opt_pp = getenv("WETTS_TC16P_PINGPONG") ? atoi(getenv("WETTS_TC16P_PINGPONG")) : 1;
   p.tmem_cols = pl.tmem_cols; p.G = pl.tmem_cols / (MB * 2 * pl.N);
+  if (opt_pp && p.G >= 2) { p.G = p.G / 2; p.acc_slots = 2; }
   p.n_abuf = na; p.n_bbuf = nb;
+  static const int opt_aw = getenv("WETTS_TC16P_ALLWARPS") ? atoi(getenv("WETTS_TC16P_ALLWARPS")) : 2;
+  static const int opt_nt_minor = getenv("WETTS_TC16_NTMINOR") ? atoi(getenv("WETTS_TC16_NTMINOR")) : 1;
+  static const int opt_prefetch = getenv("WETTS_TC16_PREFETCH") ? atoi(getenv("WETTS_TC16_PREFETCH")) : 1;
+  p.all_warps = (opt_aw == 2) ? (p.acc_slots == 2 ? 0 : 1) : opt_aw;   // 2 (default): dedicated drain warps when they can overlap the MMAs
+  p.nt_minor = (opt_nt_minor && pl.n_chunks > 1 && pl.n_tiles > 1) ? 1 : 0;
+  p.l2_prefetch = opt_prefetch;
   static const int opt_skip = getenv("WETTS_TC16_DEBUG_SKIP") ? atoi(getenv("WETTS_TC16_DEBUG_SKIP")) : 0;
   p.debug_skip = opt_skip; p.R_pad = (R + 7) & ~7;
   static DynSmemAttr attr;

@@ -40,22 +40,6 @@ WETTS_DEVICE float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const f
 WETTS_DEVICE int ldg_i32(const int* p) { return __ldg(p); }
 WETTS_DEVICE long long ldg_i64(const long long* p) { return __ldg(p); }
 
-// Warm L2 with the 128-byte lines that hold floats [t0, t1) of `nrows` rows spaced `row_stride` floats apart (fire and
-// forget; the caller's threads share the lines round-robin).  Used one work item ahead by the per-layer kernels: the
-// staging loads of an item then pay an L2 hit, not a DRAM round trip, per chunk.
-WETTS_DEVICE void l2_prefetch_rows(const float* base, long long row_stride, int nrows, int t0, int t1, int tid, int nthreads) {
-#ifndef WETTS_EMULATE
-  if (t1 <= t0 || nrows <= 0) return;
-  const int lines = ((t1 - t0) >> 5) + 2;                  // an unaligned run of n floats touches at most n/32 + 2 lines
-  const int total = nrows * lines;
-  for (int i = tid; i < total; i += nthreads) {
-    const int r = i / lines, l = i - r * lines;
-    const float* row = base + (long long)r * row_stride;
-    const uintptr_t line = (reinterpret_cast<uintptr_t>(row + t0) & ~(uintptr_t)127) + (uintptr_t)l * 128u;
-    if (line < reinterpret_cast<uintptr_t>(row + t1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-  }
-#endif
-}
 WETTS_DEVICE void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -268,6 +252,23 @@ WETTS_DEVICE void f16x2_unpack(uint32_t v, float& lo_elem, float& hi_elem) {
 
 namespace wetts {
 namespace tc {
+
+// Warm L2 with the 128-byte lines that hold floats [t0, t1) of `nrows` rows spaced `row_stride` floats apart (fire and
+// forget; the caller's threads share the lines round-robin).  Used one work item ahead by the per-layer kernels: the
+// staging loads of an item then pay an L2 hit, not a DRAM round trip, per chunk.
+WETTS_DEVICE void l2_prefetch_rows(const float* base, long long row_stride, int nrows, int t0, int t1, int tid, int nthreads) {
+#ifndef WETTS_EMULATE
+  if (t1 <= t0 || nrows <= 0) return;
+  const int lines = ((t1 - t0) >> 5) + 2;                  // an unaligned run of n floats touches at most n/32 + 2 lines
+  const int total = nrows * lines;
+  for (int i = tid; i < total; i += nthreads) {
+    const int r = i / lines, l = i - r * lines;
+    const float* row = base + (long long)r * row_stride;
+    const uintptr_t line = (reinterpret_cast<uintptr_t>(row + t0) & ~(uintptr_t)127) + (uintptr_t)l * 128u;
+    if (line < reinterpret_cast<uintptr_t>(row + t1)) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+  }
+#endif
+}
 
 // fp32 -> two fp16 operands with the same 22 significand bits as the 3xTF32 split:  x ~ hi + lo' * 2^-11,
 // hi = f16(x), lo' = f16((x - hi) * 2^11).  The lo' parts of BOTH operands carry the 2^11 scale, so the two small
