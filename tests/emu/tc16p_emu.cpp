@@ -74,7 +74,7 @@ int main(int argc, char** argv) {
   if (tc16p_smem_bytes(K, dil, N, KC, MB, na, nbuf) > emu::kSmemBytes) { printf("smem over budget\n"); return 64; }
   printf("rings: %d activation slots, %d weight slots; all_warps=%d nt_minor=%d acc_slots=%d G=%d\n", na, nbuf, p.all_warps, p.nt_minor, p.acc_slots, G);
   unsigned long long n_mma = 0;
-  emu::launch(conv1d_tc16p_kernel, p, grid, kTc16pThreads, &n_mma);
+  emu::launch(conv1d_tc16p_kernel<false>, p, grid, kTc16pThreads, &n_mma);
   // reference
   double max_err = 0, sq = 0;
   long long cnt = 0;

@@ -76,8 +76,10 @@ struct TcConvArgs {
   const float* wtc;
   int N, n_tiles, KC, n_chunks, MB, G, n_abuf, n_bbuf, R_pad, tmem_cols;
   int nt_minor = 0;     // work items ordered (rows, N tile) instead of (N tile, rows): the tiles of one row block run side by side
+  long long* prof = nullptr;   // pipelined kernel, profiling instantiation: [cta][role 0..3][9] cycle counters
   int acc_slots = 1;    // pipelined kernel: accumulator sets in TMEM (2 = the MMAs of the next item overlap the drain of this one)
   int all_warps = 0;    // pipelined kernel (tc16p): 1 = warps 2..15 stage and warps 4..15 drain, 0 = 6 stager + 8 epilogue warps
+  int epi_preload = 0;  // per-layer kernel: the epilogue's residual / skip / coupling operand is loaded before the accumulators are waited for
   int debug_skip = 0;   // experiments only (WETTS_TC16_DEBUG_SKIP): 1 = no staging work, 2 = no epilogue work (wrong results)
   int l2_prefetch = 0;  // warm L2 one work item ahead (activations) and for this item's epilogue operands
 };

@@ -43,12 +43,13 @@ using namespace tc;   // PTX wrappers shared with the fused kernels (tc_prims.cu
 // Fused epilogue of one 16-channel slice of one output row, specialised per mode with the switch
 // hoisted out of the element loops: all global loads of the slice are issued before the first store.
 // v[i] already contains bias (+ conditioning).
+template <int MODE>
 __device__ __forceinline__ void tc16_epilogue_slice(const ConvArgs& a, int b, int t, int co0, float* v, float msk) {
   const ConvEpilogue& e = a.ep;
   const size_t Ts = (size_t)a.T;
   const size_t row = (size_t)b * (size_t)e.out_bs + (size_t)t;
   const int nval = min(16, a.Cout - co0);
-  switch (e.mode) {
+  switch (MODE) {
     case EPI_PLAIN: {
       float* op = e.out + row + (size_t)co0 * Ts;
 #pragma unroll
@@ -170,6 +171,108 @@ __device__ __forceinline__ void tc16_epilogue_slice(const ConvArgs& a, int b, in
   }
 }
 
+// The operand a slice's epilogue adds to (residual, skip accumulator, residual stream, coupling target): pointer to
+// its first element and the stride between channels; false when the mode reads nothing (or reads `out`, see EPI_MRF).
+template <int MODE>
+__device__ __forceinline__ bool tc16_epilogue_operand(const ConvArgs& a, int b, int t, int co0, const float*& ptr, long long& step) {
+  const ConvEpilogue& e = a.ep;
+  const size_t Ts = (size_t)a.T;
+  const size_t row = (size_t)b * (size_t)e.out_bs + (size_t)t;
+  step = (long long)Ts;
+  switch (MODE) {
+    case EPI_RESID:
+    case EPI_MRF:
+      ptr = e.resid + row + (size_t)co0 * Ts;
+      return true;
+    case EPI_RES_SKIP:
+      if (!e.last && co0 < e.H) { ptr = e.x + row + (size_t)co0 * Ts; return true; }
+      if (e.skip_init) return false;
+      ptr = e.skip + row + (size_t)(e.last ? co0 : co0 - e.H) * Ts;
+      return true;
+    case EPI_COUPLING:
+      ptr = e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts;
+      step = (long long)e.z_cstep * (long long)Ts;
+      return true;
+    default:
+      return false;
+  }
+}
+
+// issue the loads of one slice's operand (row t, channels co0 .. co0+15) into r; zeros where nothing is read
+template <int MODE>
+__device__ __forceinline__ void tc16_epilogue_preload(const ConvArgs& a, bool active, int b, int t, int co0, float (&r)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r[i] = 0.f;
+  const float* ptr;
+  long long step;
+  if (active && t < a.T && co0 < a.Cout && tc16_epilogue_operand<MODE>(a, b, t, co0, ptr, step)) {
+    const int nval = min(16, a.Cout - co0);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nval) r[i] = ptr[(long long)i * step];
+  }
+}
+
+// tc16_epilogue_slice with the operand already in registers (r[i] = 0 where it was not read): the loads were issued before
+// the accumulators were waited for, so their latency overlaps the last MMAs instead of sitting between TMEM and the stores.
+template <int MODE>
+__device__ __forceinline__ void tc16_epilogue_slice_r(const ConvArgs& a, int b, int t, int co0, float* v, float msk, const float* r) {
+  const ConvEpilogue& e = a.ep;
+  const size_t Ts = (size_t)a.T;
+  const size_t row = (size_t)b * (size_t)e.out_bs + (size_t)t;
+  const int nval = min(16, a.Cout - co0);
+  switch (MODE) {
+    case EPI_RESID: {
+      float* op = e.out + row + (size_t)co0 * Ts;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nval) op[(size_t)i * Ts] = v[i] + r[i];
+      break;
+    }
+    case EPI_MRF: {
+      float* op = e.out + row + (size_t)co0 * Ts;
+      float o[16];
+      if (e.acc_mode != 0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = (i < nval) ? op[(size_t)i * Ts] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x = v[i] + r[i];
+        if (e.acc_mode == 1) x = o[i] + x;
+        else if (e.acc_mode == 2) x = (o[i] + x) / e.div;
+        if (i < nval) op[(size_t)i * Ts] = x;
+      }
+      break;
+    }
+    case EPI_RES_SKIP: {
+      if (!e.last && co0 < e.H) {
+        float* xp = e.x + row + (size_t)co0 * Ts;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nval) xp[(size_t)i * Ts] = (r[i] + v[i]) * msk;
+      } else {
+        float* sp = e.skip + row + (size_t)(e.last ? co0 : co0 - e.H) * Ts;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i < nval) sp[(size_t)i * Ts] = e.skip_init ? v[i] : r[i] + v[i];
+      }
+      break;
+    }
+    case EPI_COUPLING: {
+      float* zp = e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts;
+      const long long step = (long long)e.z_cstep * (long long)Ts;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < nval) zp[(long long)i * step] = (r[i] - v[i] * msk) * msk;
+      break;
+    }
+    default:
+      tc16_epilogue_slice<MODE>(a, b, t, co0, v, msk);
+      break;
+  }
+}
+
 // Warp-specialised persistent kernel with THREADS threads (8 or 16 warps).  The last warp owns the
 // tensor pipe during the main loop: one elected lane issues the weight bulk copies and every
 // tcgen05.mma / tcgen05.commit; the other warps stage activations.  The roles meet only at mbarriers
@@ -177,7 +280,9 @@ __device__ __forceinline__ void tc16_epilogue_slice(const ConvArgs& a, int b, in
 // there is no CTA-wide barrier inside an item, so staging of the next tile, the MMAs of the current
 // one and other warps' loads overlap.  All warps then share the epilogue.
 // THREADS = 256 runs 2 CTAs/SM (256 TMEM columns each), THREADS = 512 one CTA/SM (512 columns).
-template <int THREADS, int MIN_CTAS>
+// MODE = the epilogue (EpiMode) as a template parameter: one lean, branch-free epilogue per instantiation (a run-time switch
+// inlined next to the operand preload tripled the kernel's code and spilled registers into the MMA issue loop).
+template <int THREADS, int MIN_CTAS, int MODE>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const TcConvArgs p) {
   // The issue loop of tcgen05.mma is software-bound (~115 cycles per MMA measured with clock64 timers:
   // descriptor arithmetic + R2UR moves on one warp), and with N = 32..64 there are 36-84 MMAs per tile,
@@ -286,8 +391,8 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
         if (a.bias) x = a.bias[co];
         if (a.ep.cond) {
           const float* gp = a.ep.cond + (long long)b * a.ep.cond_bs + a.ep.cond_off;
-          if (a.ep.mode == EPI_GATE) x += (co & 1) ? gp[a.ep.H + (co >> 1)] : gp[co >> 1];
-          else if (a.ep.mode == EPI_PLAIN) x += gp[co];
+          if (MODE == EPI_GATE) x += (co & 1) ? gp[a.ep.H + (co >> 1)] : gp[co >> 1];
+          else if (MODE == EPI_PLAIN) x += gp[co];
         }
       }
       av[n] = x;
@@ -404,16 +509,16 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
         const int c_lo = nt * N, c_hi = min(a.Cout, nt * N + N);
         const int r_lo = t_group0, r_hi = min(T, t_group0 + tiles * MT);
         const long long ob = (long long)b * e.out_bs;
-        if (e.mode == EPI_RESID || e.mode == EPI_MRF) {
+        if (MODE == EPI_RESID || MODE == EPI_MRF) {
           l2_prefetch_rows(e.resid + ob + (long long)c_lo * T, T, c_hi - c_lo, r_lo, r_hi, tid, STAGERS);
-          if (e.mode == EPI_MRF && e.acc_mode != 0) l2_prefetch_rows(e.out + ob + (long long)c_lo * T, T, c_hi - c_lo, r_lo, r_hi, tid, STAGERS);
-        } else if (e.mode == EPI_RES_SKIP) {
+          if (MODE == EPI_MRF && e.acc_mode != 0) l2_prefetch_rows(e.out + ob + (long long)c_lo * T, T, c_hi - c_lo, r_lo, r_hi, tid, STAGERS);
+        } else if (MODE == EPI_RES_SKIP) {
           if (!e.last && c_lo < e.H) l2_prefetch_rows(e.x + ob + (long long)c_lo * T, T, min(c_hi, e.H) - c_lo, r_lo, r_hi, tid, STAGERS);
           if (!e.skip_init && (e.last || c_hi > e.H)) {
             const int s_lo = e.last ? c_lo : max(c_lo, e.H) - e.H, s_hi = e.last ? c_hi : c_hi - e.H;
             l2_prefetch_rows(e.skip + ob + (long long)s_lo * T, T, s_hi - s_lo, r_lo, r_hi, tid, STAGERS);
           }
-        } else if (e.mode == EPI_COUPLING) {
+        } else if (MODE == EPI_COUPLING) {
           l2_prefetch_rows(e.out + ob + (long long)(e.z_c0 + c_lo * e.z_cstep) * T, (long long)e.z_cstep * T, c_hi - c_lo, r_lo, r_hi, tid, STAGERS);
         }
       }
@@ -490,38 +595,76 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
         }
       }
     }
-    // ---------------- accumulators complete -> fused epilogue (all warps)
-    mbar_wait(bar_acc, acc_count & 1);
-    acc_count += 1;
-    tc_fence_after();
+    // ---------------- fused epilogue (all warps).  A thread owns one TMEM lane (output row) per M block and ncol columns:
+    // G * MB * ncol / 16 = 4 slices of 16 channels per item whenever TMEM is fully used (every plan).
     {
       constexpr int COLSPLIT = THREADS / 128;     // warps sharing a TMEM lane quarter split the columns
       const int q = warp & 3, part = warp >> 2;
       const int ncol = N / COLSPLIT;
-      const int tiles_e = (p.debug_skip & 2) ? 0 : tiles;
-      for (int g = 0; g < tiles_e; ++g) {
-        for (int mb = 0; mb < MB; ++mb) {
-          const int t = t_group0 + g * MT + mb * 128 + q * 32 + lane;
-          const float msk = (t < len) ? 1.f : 0.f;
-          const uint32_t col0 = (uint32_t)((g * MB + mb) * 2 * N + part * ncol);
-          for (int cc = 0; cc < ncol; cc += 16) {
-            float v[16], vs[16];
-            tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col0 + cc, v);
-            tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col0 + (uint32_t)N + cc, vs);
-            tmem_ld_wait();
-            const int nl = part * ncol + cc;
-            const float4* a4 = reinterpret_cast<const float4*>(av + nl);
+      const int spb = ncol >> 4;                  // slices per M block (1, 2 or 4)
+      const int n_slices = ((p.debug_skip & 2) ? 0 : tiles) * MB * spb;
+      // What the epilogue adds to is requested early: slices 0 and 1 BEFORE the accumulators are waited for (the loads
+      // overlap the last MMAs), slices 2 and 3 as soon as the registers of slices 0 and 1 are free (two register sets:
+      // four would spill).
+      float R[2][16];
+      const bool pre = p.epi_preload && n_slices <= 4;
+      const int row0 = t_group0 + q * 32 + lane, colbase = nt * N + part * ncol;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float4 x = a4[i];
-              v[4 * i + 0] = (v[4 * i + 0] + vs[4 * i + 0] * kF16LoInv) + x.x;
-              v[4 * i + 1] = (v[4 * i + 1] + vs[4 * i + 1] * kF16LoInv) + x.y;
-              v[4 * i + 2] = (v[4 * i + 2] + vs[4 * i + 2] * kF16LoInv) + x.z;
-              v[4 * i + 3] = (v[4 * i + 3] + vs[4 * i + 3] * kF16LoInv) + x.w;
-            }
-            if (t < T && nt * N + nl < a.Cout) tc16_epilogue_slice(a, b, t, nt * N + nl, v, msk);
+      for (int sl = 0; sl < 2; ++sl) {
+        const int blk = sl / spb, cs = sl - blk * spb;            // (g * MB + mb) * 128 == g * MT + mb * 128
+        tc16_epilogue_preload<MODE>(a, pre && sl < n_slices, b, row0 + blk * 128, colbase + cs * 16, R[sl]);
+      }
+      mbar_wait(bar_acc, acc_count & 1);
+      acc_count += 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int sl = 2 * h + k;
+        if (sl < n_slices) {
+          const int blk = sl / spb, cs = sl - blk * spb;
+          const int t = row0 + blk * 128;
+          const float msk = (t < len) ? 1.f : 0.f;
+          const int nl = part * ncol + cs * 16;
+          const uint32_t col0 = (uint32_t)(blk * 2 * N + nl);
+          float v[16], vs[16];
+          tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col0, v);
+          tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col0 + (uint32_t)N, vs);
+          tmem_ld_wait();
+          const float4* a4 = reinterpret_cast<const float4*>(av + nl);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 x = a4[i];
+            v[4 * i + 0] = (v[4 * i + 0] + vs[4 * i + 0] * kF16LoInv) + x.x;
+            v[4 * i + 1] = (v[4 * i + 1] + vs[4 * i + 1] * kF16LoInv) + x.y;
+            v[4 * i + 2] = (v[4 * i + 2] + vs[4 * i + 2] * kF16LoInv) + x.z;
+            v[4 * i + 3] = (v[4 * i + 3] + vs[4 * i + 3] * kF16LoInv) + x.w;
+          }
+          if (t < T && nt * N + nl < a.Cout) {
+            if (!pre) tc16_epilogue_preload<MODE>(a, true, b, t, nt * N + nl, R[k]);     // not requested ahead: load now
+            tc16_epilogue_slice_r<MODE>(a, b, t, nt * N + nl, v, msk, R[k]);
           }
         }
+        if (h == 0) {   // this register set is free: request the operand of slice sl + 2
+          const int blk = (sl + 2) / spb, cs = (sl + 2) - blk * spb;
+          tc16_epilogue_preload<MODE>(a, pre && (sl + 2) < n_slices, b, row0 + blk * 128, colbase + cs * 16, R[k]);
+        }
+      }
+      // (plans that leave TMEM partly unused would have more than 4 slices: none exists; they would take this loop)
+      for (int sl = 4; sl < n_slices; ++sl) {
+        const int blk = sl / spb, cs = sl - blk * spb;
+        const int t = t_group0 + blk * 128 + q * 32 + lane;
+        const float msk = (t < len) ? 1.f : 0.f;
+        const int nl = part * ncol + cs * 16;
+        const uint32_t col0 = (uint32_t)(blk * 2 * N + nl);
+        float v[16], vs[16];
+        tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col0, v);
+        tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + col0 + (uint32_t)N, vs);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = (v[i] + vs[i] * kF16LoInv) + av[nl + i];
+        if (t < T && nt * N + nl < a.Cout) tc16_epilogue_slice<MODE>(a, b, t, nt * N + nl, v, msk);
       }
     }
   }
@@ -649,20 +792,39 @@ void launch_conv1d_tc16(const ConvArgs& a, cudaStream_t s) {
   p.l2_prefetch = opt_prefetch;
   static const int opt_skip = getenv("WETTS_TC16_DEBUG_SKIP") ? atoi(getenv("WETTS_TC16_DEBUG_SKIP")) : 0;
   p.debug_skip = opt_skip;
-  static DynSmemAttr attr[2];
+  static const int opt_pre = getenv("WETTS_TC16_EPI_PRELOAD") ? atoi(getenv("WETTS_TC16_EPI_PRELOAD")) : 1;
+  p.epi_preload = opt_pre;
+  static DynSmemAttr attr[2][7];
   const int n_sm = current_device_sm_count();
   if (n_sm <= 0) return;
   const int group_rows = p.G * 128 * MB;
   const long long items = (long long)a.B * ((a.T + group_rows - 1) / group_rows) * pl.n_tiles;
-  if (pl.mode == 0) {
-    if (attr[0].ensure((const void*)conv1d_tc16_kernel<256, 2>, smem) != cudaSuccess) return;
-    const int grid = (int)(items < 2 * n_sm ? items : 2 * n_sm);
-    conv1d_tc16_kernel<256, 2><<<grid, 256, smem, s>>>(p);
-  } else {
-    if (attr[1].ensure((const void*)conv1d_tc16_kernel<512, 1>, smem) != cudaSuccess) return;
-    const int grid = (int)(items < n_sm ? items : n_sm);
-    conv1d_tc16_kernel<512, 1><<<grid, 512, smem, s>>>(p);
+  const int grid = (int)(pl.mode == 0 ? (items < 2 * n_sm ? items : 2 * n_sm) : (items < n_sm ? items : n_sm));
+  bool ok = false;
+#define WETTS_TC16_LAUNCH(M)                                                                                     \
+  case M:                                                                                                        \
+    if (pl.mode == 0) {                                                                                          \
+      if (attr[0][M].ensure((const void*)conv1d_tc16_kernel<256, 2, M>, smem) != cudaSuccess) return;            \
+      conv1d_tc16_kernel<256, 2, M><<<grid, 256, smem, s>>>(p);                                                  \
+    } else {                                                                                                     \
+      if (attr[1][M].ensure((const void*)conv1d_tc16_kernel<512, 1, M>, smem) != cudaSuccess) return;            \
+      conv1d_tc16_kernel<512, 1, M><<<grid, 512, smem, s>>>(p);                                                  \
+    }                                                                                                            \
+    ok = true;                                                                                                   \
+    break;
+  switch (a.ep.mode) {
+    WETTS_TC16_LAUNCH(EPI_PLAIN)
+    WETTS_TC16_LAUNCH(EPI_RESID)
+    WETTS_TC16_LAUNCH(EPI_MRF)
+    WETTS_TC16_LAUNCH(EPI_GATE)
+    WETTS_TC16_LAUNCH(EPI_RES_SKIP)
+    WETTS_TC16_LAUNCH(EPI_COUPLING)
+    WETTS_TC16_LAUNCH(EPI_CONVT)
+    default:
+      break;
   }
+#undef WETTS_TC16_LAUNCH
+  if (!ok) return;
   count_launch();
 }
 

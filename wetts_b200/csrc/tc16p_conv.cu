@@ -1,7 +1,9 @@
 // Launch side of the pipelined per-layer f16 conv kernel (tc16p_conv_kernel.cuh).  It consumes the packed weights and
 // the tiling plan of tc16_conv_kernel.cu unchanged.
 #include <atomic>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "kernels.cuh"
 #include "tc16p_conv_kernel.cuh"
@@ -50,14 +52,45 @@ bool launch_conv1d_tc16p(const ConvArgs& a, cudaStream_t s) {
   p.l2_prefetch = opt_prefetch;
   static const int opt_skip = getenv("WETTS_TC16_DEBUG_SKIP") ? atoi(getenv("WETTS_TC16_DEBUG_SKIP")) : 0;
   p.debug_skip = opt_skip; p.R_pad = (R + 7) & ~7;
-  static DynSmemAttr attr;
-  if (attr.ensure((const void*)conv1d_tc16p_kernel, smem) != cudaSuccess) return true;   // error recorded; nothing launched
+  static DynSmemAttr attr, attr_prof;
   const int n_sm = current_device_sm_count();
   if (n_sm <= 0) return true;
   const int group_rows = p.G * 128 * MB;
   const long long items = (long long)a.B * ((a.T + group_rows - 1) / group_rows) * pl.n_tiles;
   const int grid = (int)(items < n_sm ? items : n_sm);
-  conv1d_tc16p_kernel<<<grid, kTc16pThreads, smem, s>>>(p);
+  static const int opt_prof = getenv("WETTS_TC16P_PROFILE") ? atoi(getenv("WETTS_TC16P_PROFILE")) : 0;
+  if (opt_prof) {
+    // debugging hook: clock64 phase counters of one thread per role; synchronises the stream and prints one line per launch
+    if (attr_prof.ensure((const void*)conv1d_tc16p_kernel<true>, smem) != cudaSuccess) return true;
+    const size_t n = (size_t)grid * 4 * (kTc16pProfSlots + 1);
+    long long* d = nullptr;
+    if (cudaMalloc(&d, n * sizeof(long long)) != cudaSuccess) return true;
+    cudaMemsetAsync(d, 0, n * sizeof(long long), s);
+    p.prof = d;
+    conv1d_tc16p_kernel<true><<<grid, kTc16pThreads, smem, s>>>(p);
+    count_launch();
+    if (cudaStreamSynchronize(s) == cudaSuccess) {
+      std::vector<long long> h(n);
+      cudaMemcpy(h.data(), d, n * sizeof(long long), cudaMemcpyDeviceToHost);
+      double m[4][kTc16pProfSlots + 1] = {};
+      for (int b = 0; b < grid; ++b)
+        for (int r = 0; r < 4; ++r)
+          for (int i = 0; i <= kTc16pProfSlots; ++i) m[r][i] += (double)h[((size_t)b * 4 + r) * (kTc16pProfSlots + 1) + i];
+      const double per = (double)items / grid * grid;   // items in total
+      auto v = [&](int r, int i) { return m[r][i] / per; };
+      fprintf(stderr,
+              "[tc16p profile] Cin=%d Cout=%d K=%d dil=%d T=%d B=%d ep=%d | N=%d KC=%d chunks=%d MB=%d G=%d slots=%d NA=%d NB=%d aw=%d items/CTA=%.1f | cycles/item: "
+              "total=%.0f | MMA: acc_empty=%.0f b_full=%.0f a_full=%.0f issue=%.0f | producer: b_free=%.0f | stager(w2): prefetch=%.0f tile=%.0f (a_free=%.0f) "
+              "fence+arrive=%.0f | drain(w15): acc_full=%.0f body=%.0f\n",
+              a.Cin, a.Cout, a.K, a.dil, a.T, a.B, (int)a.ep.mode, p.N, p.KC, p.n_chunks, p.MB, p.G, p.acc_slots, na, nb, p.all_warps,
+              (double)items / grid, v(0, kTc16pProfSlots), v(0, 0), v(0, 1), v(0, 2), v(0, 3), v(1, 0), v(2, 5), v(2, 2), v(2, 1), v(2, 3),
+              v(3, 6), v(3, 7));
+    }
+    cudaFree(d);
+    return true;
+  }
+  if (attr.ensure((const void*)conv1d_tc16p_kernel<false>, smem) != cudaSuccess) return true;   // error recorded; nothing launched
+  conv1d_tc16p_kernel<false><<<grid, kTc16pThreads, smem, s>>>(p);
   count_launch();
   return true;
 }

@@ -48,8 +48,16 @@ inline size_t tc16p_smem_bytes(int K, int dil, int N, int KC, int MB, int na = k
   return 192 + (size_t)na * (2 * (size_t)(KC / 8) * Rp * 16) + (size_t)nb * ((size_t)K * (KC / 8) * 2 * N * 16);
 }
 
+// PROF: clock64 phase counters of one thread per role (WETTS_TC16P_PROFILE=1; table printed by the launcher)
+constexpr int kTc16pProfSlots = 8;
+template <bool PROF>
 WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(const TcConvArgs p) {
   using namespace tc;
+  long long pc[kTc16pProfSlots];
+#pragma unroll
+  for (int i = 0; i < kTc16pProfSlots; ++i) pc[i] = 0;
+  long long t_a = 0, t_b = 0;
+  const long long t_start = PROF ? clock_now() : 0;
   constexpr int NAMAX = kTc16pNA;
   WETTS_SMEM_DECL(smem);
   const ConvArgs& a = p.c;
@@ -141,13 +149,19 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
       int nt, b, t_group0, tiles, nch;
       decode(item, nt, b, t_group0, tiles, nch);
       const uint32_t slot = it_cnt & s_log, s_use = it_cnt >> s_log;
+      if (PROF) t_a = clock_now();
       if (s_use > 0) mbar_wait(bar_acc_empty + 8 * slot, (s_use - 1) & 1);   // the slot's previous item is drained
+      if (PROF) pc[0] += clock_now() - t_a;
       tc_fence_after();
       for (int c = 0; c < nch; ++c) {
+        if (PROF) t_a = clock_now();
         mbar_wait(bar_b_full + 8 * bb, b_use & 1);
+        if (PROF) pc[1] += clock_now() - t_a;
         for (int g = 0; g < tiles; ++g) {
           const uint32_t ab = a_cnt & (NA - 1u);
+          if (PROF) t_a = clock_now();
           mbar_wait(bar_a_full + 8 * ab, (a_cnt >> na_log) & 1);
+          if (PROF) { t_b = clock_now(); pc[2] += t_b - t_a; }
           tc_fence_after();
           const uint64_t adesc0 = make_desc(A_addr + ab * a_bytes, (uint32_t)Rp * 16, 128);
           const uint64_t bdesc0 = make_desc(B_addr + bb * b_bytes, (uint32_t)(2 * N) * 16, 128);
@@ -168,6 +182,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
           }
           if (elect_one()) tc_commit(bar_a_free + 8 * ab);
           warp_sync();
+          if (PROF) pc[3] += clock_now() - t_b;
           a_cnt += 1;
         }
         if (elect_one()) tc_commit(bar_b_free + 8 * bb);
@@ -186,7 +201,9 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
       int nt, b, t_group0, tiles, nch;
       decode(item, nt, b, t_group0, tiles, nch);
       for (int c = 0; c < nch; ++c) {
+        if (PROF) t_a = clock_now();
         if (use > 0) mbar_wait(bar_b_free + 8 * bb, (use - 1) & 1);
+        if (PROF) pc[0] += clock_now() - t_a;
         warp_sync();
         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wtc) + ((size_t)nt * p.n_chunks + c) * b_bytes;
         if (elect_one()) {
@@ -218,6 +235,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
       if (do_stage) {
         const int t_hi = a.in_mask ? (int)(len < Tin ? len : Tin) : Tin;
         const float* in_b = a.in + (long long)b * a.in_bs;
+        if (PROF) t_a = clock_now();
         if (p.l2_prefetch) {
           // the activation rows of this CTA's next item and what this item's epilogue reads back, into L2
           const int nxt = item + (int)WETTS_NBLK;
@@ -231,10 +249,12 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
           }
           tc_epilogue_prefetch(a, b, nt * N, ep_min(a.Cout, nt * N + N), t_group0, ep_min(T, t_group0 + tiles * MT), st, n_stagers);
         }
+        if (PROF) pc[5] += clock_now() - t_a;
         for (int c = 0; c < nch; ++c) {
           const int c0 = c * KC;
           for (int g = 0; g < tiles; ++g) {
             const uint32_t ab = a_cnt & (NA - 1u), use = a_cnt >> na_log;
+            if (PROF) t_a = clock_now();
             uint8_t* Ah = A0 + (size_t)ab * a_bytes;
             const int t_in0 = t_group0 + g * MT - a.pad_left;
             bool waited = (use == 0);
@@ -258,7 +278,9 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
                 for (int e = 0; e < 16; ++e) v[k][e] = (rok && (ci0 + e) < a.Cin) ? ldg(src + (long long)e * a.in_cs) : 0.f;
               }
               if (!waited) {   // the MMAs that last read this slot must be done before it is overwritten
+                if (PROF) t_b = clock_now();
                 mbar_wait(bar_a_free + 8 * ab, (use - 1) & 1);
+                if (PROF) pc[1] += clock_now() - t_b;
                 waited = true;
               }
 #pragma unroll
@@ -285,16 +307,20 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
               }
             }
             if (!waited) mbar_wait(bar_a_free + 8 * ab, (use - 1) & 1);
+            if (PROF) t_b = clock_now();
             fence_async_smem();
             warp_sync();
             if (lane == 0) mbar_arrive(bar_a_full + 8 * ab);
+            if (PROF) { const long long t_c = clock_now(); pc[3] += t_c - t_b; pc[2] += t_b - t_a; }   // [2] includes [1]
             a_cnt += 1;
           }
         }
       }
       if (do_epi) {
         const uint32_t slot = it_cnt & s_log, s_use = it_cnt >> s_log;
+        if (PROF) t_a = clock_now();
         mbar_wait(bar_acc_full + 8 * slot, s_use & 1);
+        if (PROF) { t_b = clock_now(); pc[6] += t_b - t_a; }
         tc_fence_after();
         const int tiles_e = (p.debug_skip & 2) ? 0 : tiles;
         for (int g = 0; g < tiles_e; ++g) {
@@ -329,9 +355,17 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kTc16pThreads, 1) conv1d_tc16p_kernel(cons
         tc_fence_before();
         warp_sync();
         if (lane == 0) mbar_arrive(bar_acc_empty + 8 * slot);
+        if (PROF) pc[7] += clock_now() - t_b;
         it_cnt += 1;
       }
     }
+  }
+  if (PROF && p.prof && lane == 0 && (warp == 0 || warp == 1 || warp == 2 || warp == 15)) {
+    // role rows: 0 MMA issuer, 1 weight producer, 2 first stager warp, 3 last worker warp (drains in both assignments)
+    const int role = warp == 15 ? 3 : warp;
+    long long* dst = p.prof + ((size_t)WETTS_BID * 4 + role) * (kTc16pProfSlots + 1);
+    for (int i = 0; i < kTc16pProfSlots; ++i) dst[i] = pc[i];
+    dst[kTc16pProfSlots] = clock_now() - t_start;
   }
   tc_fence_before();
   cta_sync();
