@@ -79,6 +79,8 @@ struct TcConvArgs {
   long long* prof = nullptr;   // pipelined kernel, profiling instantiation: [cta][role 0..3][9] cycle counters
   int acc_slots = 1;    // pipelined kernel: accumulator sets in TMEM (2 = the MMAs of the next item overlap the drain of this one)
   int all_warps = 0;    // pipelined kernel (tc16p): 1 = warps 2..15 stage and warps 4..15 drain, 0 = 6 stager + 8 epilogue warps
+  int stagger = 0;      // per-layer kernel: CTA i starts (i % 8) * stagger / 8 cycles late, so that the CTAs' memory-bound phases
+                        // (staging, epilogue) and tensor-bound phases (MMAs) do not all coincide on the chip
   int epi_preload = 0;  // per-layer kernel: the epilogue's residual / skip / coupling operand is loaded before the accumulators are waited for
   int debug_skip = 0;   // experiments only (WETTS_TC16_DEBUG_SKIP): 1 = no staging work, 2 = no epilogue work (wrong results)
   int l2_prefetch = 0;  // warm L2 one work item ahead (activations) and for this item's epilogue operands

@@ -43,81 +43,95 @@ using namespace tc;   // PTX wrappers shared with the fused kernels (tc_prims.cu
 // Fused epilogue of one 16-channel slice of one output row, specialised per mode with the switch
 // hoisted out of the element loops: all global loads of the slice are issued before the first store.
 // v[i] already contains bias (+ conditioning).
+// N strided loads / stores (channel stride `step` floats) with one 64-bit add per element and, for a full slice, no
+// per-element predicate (the per-element `i < nval` test + 64-bit multiply cost 13 instructions per store, and the kernel
+// is issue bound: 79 k warp-instructions per 256-row item at 4 warps per scheduler).
+template <int NE>
+__device__ __forceinline__ void ld_strided(const float* p, long long step, int nval, float (&r)[16]) {
+  if (nval >= NE) {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { r[i] = *p; p += step; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { r[i] = (i < nval) ? *p : 0.f; p += step; }
+  }
+}
+template <int NE>
+__device__ __forceinline__ void st_strided(float* p, long long step, int nval, const float (&x)[16]) {
+  if (nval >= NE) {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { *p = x[i]; p += step; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { if (i < nval) *p = x[i]; p += step; }
+  }
+}
+
 template <int MODE>
 __device__ __forceinline__ void tc16_epilogue_slice(const ConvArgs& a, int b, int t, int co0, float* v, float msk) {
   const ConvEpilogue& e = a.ep;
   const size_t Ts = (size_t)a.T;
+  const long long step = (long long)Ts;
   const size_t row = (size_t)b * (size_t)e.out_bs + (size_t)t;
   const int nval = min(16, a.Cout - co0);
+  float x[16], r[16];
   switch (MODE) {
     case EPI_PLAIN: {
-      float* op = e.out + row + (size_t)co0 * Ts;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float x = v[i];
-        if (e.act == 1) x = fmaxf(x, 0.f);
-        else if (e.act == 2) x = gelu_erf_acc(x);
-        if (e.out_mask) x *= msk;
-        if (i < nval) op[(size_t)i * Ts] = x;
+        x[i] = v[i];
+        if (e.act == 1) x[i] = fmaxf(x[i], 0.f);
+        else if (e.act == 2) x[i] = gelu_erf_acc(x[i]);
+        if (e.out_mask) x[i] *= msk;
       }
+      st_strided<16>(e.out + row + (size_t)co0 * Ts, step, nval, x);
       break;
     }
     case EPI_RESID: {
-      const float* rp = e.resid + row + (size_t)co0 * Ts;
-      float* op = e.out + row + (size_t)co0 * Ts;
-      float r[16];
+      ld_strided<16>(e.resid + row + (size_t)co0 * Ts, step, nval, r);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? rp[(size_t)i * Ts] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nval) op[(size_t)i * Ts] = v[i] + r[i];
+      for (int i = 0; i < 16; ++i) x[i] = v[i] + r[i];
+      st_strided<16>(e.out + row + (size_t)co0 * Ts, step, nval, x);
       break;
     }
     case EPI_MRF: {
-      const float* rp = e.resid + row + (size_t)co0 * Ts;
       float* op = e.out + row + (size_t)co0 * Ts;
-      float r[16], o[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? rp[(size_t)i * Ts] : 0.f;
-      if (e.acc_mode != 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = (i < nval) ? op[(size_t)i * Ts] : 0.f;
-      }
+      float o[16];
+      ld_strided<16>(e.resid + row + (size_t)co0 * Ts, step, nval, r);
+      if (e.acc_mode != 0) ld_strided<16>(op, step, nval, o);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float x = v[i] + r[i];
-        if (e.acc_mode == 1) x = o[i] + x;
-        else if (e.acc_mode == 2) x = (o[i] + x) / e.div;
-        if (i < nval) op[(size_t)i * Ts] = x;
+        x[i] = v[i] + r[i];
+        if (e.acc_mode == 1) x[i] = o[i] + x[i];
+        else if (e.acc_mode == 2) x[i] = (o[i] + x[i]) / e.div;
       }
+      st_strided<16>(op, step, nval, x);
       break;
     }
     case EPI_GATE: {
-      float* op = e.out + row + (size_t)(co0 >> 1) * Ts;
 #pragma unroll
-      for (int i = 0; i < 16; i += 2)
-        if (i < nval) op[(size_t)(i >> 1) * Ts] = gate_tanh_sigmoid_fast(v[i], v[i + 1]);
+      for (int i = 0; i < 8; ++i) x[i] = gate_tanh_sigmoid_fast(v[2 * i], v[2 * i + 1]);
+      st_strided<8>(e.out + row + (size_t)(co0 >> 1) * Ts, step, (nval + 1) >> 1, x);
       break;
     }
     case EPI_RES_SKIP: {
       if (!e.last && co0 < e.H) {  // residual stream (a 16-slice never straddles H: H % 16 == 0 is checked on the host)
         float* xp = e.x + row + (size_t)co0 * Ts;
-        float r[16];
+        ld_strided<16>(xp, step, nval, r);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? xp[(size_t)i * Ts] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < nval) xp[(size_t)i * Ts] = (r[i] + v[i]) * msk;
+        for (int i = 0; i < 16; ++i) x[i] = (r[i] + v[i]) * msk;
+        st_strided<16>(xp, step, nval, x);
       } else {
         float* sp = e.skip + row + (size_t)(e.last ? co0 : co0 - e.H) * Ts;
-        float r[16];
         if (!e.skip_init) {
+          ld_strided<16>(sp, step, nval, r);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? sp[(size_t)i * Ts] : 0.f;
+          for (int i = 0; i < 16; ++i) x[i] = r[i] + v[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = v[i];
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < nval) sp[(size_t)i * Ts] = e.skip_init ? v[i] : r[i] + v[i];
+        st_strided<16>(sp, step, nval, x);
       }
       break;
     }
@@ -157,13 +171,11 @@ __device__ __forceinline__ void tc16_epilogue_slice(const ConvArgs& a, int b, in
     }
     case EPI_COUPLING: {
       float* zp = e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts;
-      const long long step = (long long)e.z_cstep * (long long)Ts;
-      float r[16];
+      const long long zstep = (long long)e.z_cstep * (long long)Ts;
+      ld_strided<16>(zp, zstep, nval, r);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? zp[(long long)i * step] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nval) zp[(long long)i * step] = (r[i] - v[i] * msk) * msk;
+      for (int i = 0; i < 16; ++i) x[i] = (r[i] - v[i] * msk) * msk;
+      st_strided<16>(zp, zstep, nval, x);
       break;
     }
     default:
@@ -203,68 +215,57 @@ template <int MODE>
 __device__ __forceinline__ void tc16_epilogue_preload(const ConvArgs& a, bool active, int b, int t, int co0, float (&r)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) r[i] = 0.f;
-  const float* ptr;
+  const float* ptr = nullptr;
   long long step;
-  if (active && t < a.T && co0 < a.Cout && tc16_epilogue_operand<MODE>(a, b, t, co0, ptr, step)) {
-    const int nval = min(16, a.Cout - co0);
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nval) r[i] = ptr[(long long)i * step];
-  }
+  if (active && t < a.T && co0 < a.Cout && tc16_epilogue_operand<MODE>(a, b, t, co0, ptr, step)) ld_strided<16>(ptr, step, min(16, a.Cout - co0), r);
 }
 
 // tc16_epilogue_slice with the operand already in registers (r[i] = 0 where it was not read): the loads were issued before
 // the accumulators were waited for, so their latency overlaps the last MMAs instead of sitting between TMEM and the stores.
 template <int MODE>
-__device__ __forceinline__ void tc16_epilogue_slice_r(const ConvArgs& a, int b, int t, int co0, float* v, float msk, const float* r) {
+__device__ __forceinline__ void tc16_epilogue_slice_r(const ConvArgs& a, int b, int t, int co0, float* v, float msk, const float (&r)[16]) {
   const ConvEpilogue& e = a.ep;
   const size_t Ts = (size_t)a.T;
+  const long long step = (long long)Ts;
   const size_t row = (size_t)b * (size_t)e.out_bs + (size_t)t;
   const int nval = min(16, a.Cout - co0);
+  float x[16];
   switch (MODE) {
     case EPI_RESID: {
-      float* op = e.out + row + (size_t)co0 * Ts;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nval) op[(size_t)i * Ts] = v[i] + r[i];
+      for (int i = 0; i < 16; ++i) x[i] = v[i] + r[i];
+      st_strided<16>(e.out + row + (size_t)co0 * Ts, step, nval, x);
       break;
     }
     case EPI_MRF: {
       float* op = e.out + row + (size_t)co0 * Ts;
       float o[16];
-      if (e.acc_mode != 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = (i < nval) ? op[(size_t)i * Ts] : 0.f;
-      }
+      if (e.acc_mode != 0) ld_strided<16>(op, step, nval, o);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float x = v[i] + r[i];
-        if (e.acc_mode == 1) x = o[i] + x;
-        else if (e.acc_mode == 2) x = (o[i] + x) / e.div;
-        if (i < nval) op[(size_t)i * Ts] = x;
+        x[i] = v[i] + r[i];
+        if (e.acc_mode == 1) x[i] = o[i] + x[i];
+        else if (e.acc_mode == 2) x[i] = (o[i] + x[i]) / e.div;
       }
+      st_strided<16>(op, step, nval, x);
       break;
     }
     case EPI_RES_SKIP: {
       if (!e.last && co0 < e.H) {
-        float* xp = e.x + row + (size_t)co0 * Ts;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < nval) xp[(size_t)i * Ts] = (r[i] + v[i]) * msk;
+        for (int i = 0; i < 16; ++i) x[i] = (r[i] + v[i]) * msk;
+        st_strided<16>(e.x + row + (size_t)co0 * Ts, step, nval, x);
       } else {
-        float* sp = e.skip + row + (size_t)(e.last ? co0 : co0 - e.H) * Ts;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < nval) sp[(size_t)i * Ts] = e.skip_init ? v[i] : r[i] + v[i];
+        for (int i = 0; i < 16; ++i) x[i] = e.skip_init ? v[i] : r[i] + v[i];
+        st_strided<16>(e.skip + row + (size_t)(e.last ? co0 : co0 - e.H) * Ts, step, nval, x);
       }
       break;
     }
     case EPI_COUPLING: {
-      float* zp = e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts;
-      const long long step = (long long)e.z_cstep * (long long)Ts;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nval) zp[(long long)i * step] = (r[i] - v[i] * msk) * msk;
+      for (int i = 0; i < 16; ++i) x[i] = (r[i] - v[i] * msk) * msk;
+      st_strided<16>(e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts, (long long)e.z_cstep * (long long)Ts, nval, x);
       break;
     }
     default:
@@ -333,6 +334,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
     for (int i = 0; i < 4; ++i) mbar_init(bar_a_full + 8 * i, STAGERS / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // Every CTA runs the same sequence of equally long items (stage -> MMAs -> epilogue): started together they hit DRAM
+  // in the same bursts and leave it idle during the MMAs.  A start-up offset per CTA spreads the phases over time.
+  if (p.stagger > 0) spin_cycles(((long long)(blockIdx.x & 7) * p.stagger) >> 3);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -493,6 +497,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
       const int Tin = a.in_T > 0 ? a.in_T : T;
       const int t_hi = a.in_mask ? (int)(len < Tin ? len : Tin) : Tin;
       const float* in_b = a.in + (long long)b * a.in_bs;
+      const long long in_cs = a.in_cs;
       if (p.l2_prefetch) {
         // (1) the activation rows of this CTA's NEXT item: its staging loads (16 per thread and round, one round trip per
         // chunk on the critical path of the MMAs) then hit L2; (2) what this item's epilogue reads back.
@@ -547,9 +552,13 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
               const bool rok = (u2 == 0 || has_b) && (rr[u2] < R) && (t >= 0) && (t < t_hi);
               const int ci0 = c0 + qq[u2] * 16;
               const float* src = in_b + (long long)ci0 * a.in_cs + t;
-              if (fast) {
+              if (fast) {      // one 64-bit add per load instead of a 64-bit multiply-add (issue-bound kernel)
+                const float* sp = src;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) v[u2][e] = rok ? __ldg(src + (long long)e * a.in_cs) : 0.f;
+                for (int e = 0; e < 16; ++e) {
+                  v[u2][e] = rok ? __ldg(sp) : 0.f;
+                  sp += in_cs;
+                }
               } else {
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
@@ -737,6 +746,27 @@ bool tc16_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
         }
       }
   }
+  // ---- mode 2 ("two CTAs", WETTS_TC16_TWO_CTAS=1 at load time): the large-mode tiling with one M block per item, 256 TMEM
+  // columns, 256 threads and <= 112 KB, so that two CTAs share an SM and one's MMAs run during the other's staging and
+  // epilogue (the phases of an item cannot overlap inside a CTA: its accumulators fill its TMEM).  Costs twice the weight
+  // stream per output row.
+  static const int two_ctas = getenv("WETTS_TC16_TWO_CTAS") ? atoi(getenv("WETTS_TC16_TWO_CTAS")) : 0;
+  if (two_ctas) {
+    const int cout64b = (Cout + 63) / 64 * 64;
+    for (int n_tiles = (cout64b + 127) / 128; n_tiles <= cout64b / 64; ++n_tiles) {
+      const int N = ((cout64b + n_tiles - 1) / n_tiles + 63) / 64 * 64;
+      if (N > 128) continue;
+      for (int nch = 1; nch <= cin16 / 16; ++nch) {
+        const int KC = ((cin16 + nch - 1) / nch + 15) / 16 * 16;
+        const int nb = (cin16 + KC - 1) / KC == 1 ? 1 : 2;
+        if (tc16_conv_smem_bytes(K, dil, N, KC, 1, 2, nb) <= 112 * 1024) {
+          fill(1, N, n_tiles, KC, 1, 2, nb);
+          plan->mode = 2; plan->tmem_cols = 256; plan->G = 256 / (2 * N);
+          return true;
+        }
+      }
+    }
+  }
   // ---- large mode (N a multiple of 64 so that 16 warps split the columns in 16-wide pieces)
   // WETTS_TC16_NMAX=64 (read once, at load time): 64-wide N tiles, so that two items' accumulators fit in TMEM and the
   // pipelined kernel can drain one while the MMAs of the next run
@@ -792,6 +822,7 @@ void launch_conv1d_tc16(const ConvArgs& a, cudaStream_t s) {
   p.l2_prefetch = opt_prefetch;
   static const int opt_skip = getenv("WETTS_TC16_DEBUG_SKIP") ? atoi(getenv("WETTS_TC16_DEBUG_SKIP")) : 0;
   p.debug_skip = opt_skip;
+  static const int opt_stagger = getenv("WETTS_TC16_STAGGER") ? atoi(getenv("WETTS_TC16_STAGGER")) : 0;
   static const int opt_pre = getenv("WETTS_TC16_EPI_PRELOAD") ? atoi(getenv("WETTS_TC16_EPI_PRELOAD")) : 1;
   p.epi_preload = opt_pre;
   static DynSmemAttr attr[2][7];
@@ -799,11 +830,13 @@ void launch_conv1d_tc16(const ConvArgs& a, cudaStream_t s) {
   if (n_sm <= 0) return;
   const int group_rows = p.G * 128 * MB;
   const long long items = (long long)a.B * ((a.T + group_rows - 1) / group_rows) * pl.n_tiles;
-  const int grid = (int)(pl.mode == 0 ? (items < 2 * n_sm ? items : 2 * n_sm) : (items < n_sm ? items : n_sm));
+  p.stagger = (items > 2LL * n_sm) ? opt_stagger : 0;   // only launches with several items per CTA
+  const bool two = (pl.mode == 0 || pl.mode == 2);      // 256-thread CTAs, two per SM
+  const int grid = (int)(two ? (items < 2 * n_sm ? items : 2 * n_sm) : (items < n_sm ? items : n_sm));
   bool ok = false;
 #define WETTS_TC16_LAUNCH(M)                                                                                     \
   case M:                                                                                                        \
-    if (pl.mode == 0) {                                                                                          \
+    if (two) {                                                                                                   \
       if (attr[0][M].ensure((const void*)conv1d_tc16_kernel<256, 2, M>, smem) != cudaSuccess) return;            \
       conv1d_tc16_kernel<256, 2, M><<<grid, 256, smem, s>>>(p);                                                  \
     } else {                                                                                                     \
