@@ -31,8 +31,19 @@ import sys
 import threading
 import time
 
-# NCCL prints its version banner on stdout; the contract is ONE JSON line there, so send NCCL's log to stderr
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on fd 1 even with
+# NCCL_DEBUG_FILE set -- seen on the 2-GPU box), so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+# a private duplicate of the original stdout.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 import torch  # noqa: E402
 
@@ -297,7 +308,7 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": threads, "kind": arm.kind, "sample": sample},
         "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -608,7 +619,7 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "gpu_eager_baseline": gpu_eager,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist:
         dist.destroy_process_group()
 
