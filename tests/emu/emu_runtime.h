@@ -252,7 +252,8 @@ WETTS_DEVICE void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(50));
     else std::this_thread::yield();
     if ((spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(emu::wait_timeout_s())) {
-      fprintf(stderr, "mbarrier 0x%x parity %u\n", bar, parity);
+      fprintf(stderr, "mbarrier 0x%x parity %u (block %d thread %d)\n", bar, parity, emu::cta()->bid, emu::g_tid);
+      if (getenv("EMU_DEADLOCK_DUMP")) std::this_thread::sleep_for(std::chrono::seconds(5));   // let the other waiters report too
       emu::die("mbarrier wait timed out (deadlock)");
     }
   }

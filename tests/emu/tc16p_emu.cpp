@@ -19,7 +19,7 @@ int main(int argc, char** argv) {
   const int cin16 = (Cin + 15) / 16 * 16, n_chunks = (cin16 + KC - 1) / KC, n_tiles = (Cout + N - 1) / N;
   const int MB = 2, tmem_cols = 512;
   int G = tmem_cols / (MB * 2 * N);
-  const int pp = (getenv("EMU_PINGPONG") ? atoi(getenv("EMU_PINGPONG")) : 1) && G >= 2;
+  const int pp = (getenv("EMU_PINGPONG") ? atoi(getenv("EMU_PINGPONG")) : 0) && G >= 2;
   if (pp) G /= 2;
   if (G < 1 || (N % 32) || (KC % 16)) { printf("bad tiling\n"); return 64; }
   std::mt19937 rng(7 + Cin + Cout + T);
@@ -68,7 +68,7 @@ int main(int argc, char** argv) {
   p.N = N; p.n_tiles = n_tiles; p.KC = KC; p.n_chunks = n_chunks; p.MB = MB; p.G = G; p.n_abuf = na; p.n_bbuf = nbuf;
   p.R_pad = (R + 7) & ~7; p.tmem_cols = tmem_cols;
   p.acc_slots = pp ? 2 : 1;
-  p.all_warps = getenv("EMU_ALLWARPS") ? atoi(getenv("EMU_ALLWARPS")) : (pp ? 0 : 1);
+  p.all_warps = getenv("EMU_ALLWARPS") ? atoi(getenv("EMU_ALLWARPS")) : 1;
   p.nt_minor = (getenv("EMU_NTMINOR") ? atoi(getenv("EMU_NTMINOR")) : 1) && n_chunks > 1 && n_tiles > 1;
   p.l2_prefetch = 1;
   if (tc16p_smem_bytes(K, dil, N, KC, MB, na, nbuf) > emu::kSmemBytes) { printf("smem over budget\n"); return 64; }

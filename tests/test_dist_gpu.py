@@ -1,7 +1,8 @@
 """world_size-2 NCCL test of the serving-side sharding (wetts_b200/dist.py) on two real GPUs: rank 0 holds the batch,
 ids (and the injected per-utterance noise) are scattered over NCCL, both ranks synthesise their shard with the CUDA
-engine, waveforms are gathered back to rank 0 and must be BIT-identical to the unsharded run on rank 0's GPU
-(SURVEY.md 8e parity caveat: explicit per-utterance noise).  Skipped on boxes with fewer than two GPUs
+engine, waveforms are gathered back to rank 0 and must be BIT-identical to the unsharded run on rank 0's GPU (SURVEY.md 8e parity caveat:
+explicit per-utterance noise), except inside the vocoder's receptive field of the end of a shard's longest utterance
+(the reference model's own dependence on batch padding; see the comment in the worker).  Skipped on boxes with fewer than two GPUs
 (run it with `gpurun --gpus 2 -- python -m pytest tests/test_dist_gpu.py -m gpu`)."""
 import os
 import socket
@@ -52,14 +53,26 @@ def _worker(rank, world, port, ret):
                         noise_z=noise_z if on0 else None, durations=dur if on0 else None, **kw)
     if on0:
         o, _, ym, _ = net.infer(x, lens, sid, noise_z=noise_z, durations=dur, **kw)
+        # Bit-identical, with the one exception the reference model has too: HiFi-GAN does not mask, so the last samples of
+        # an utterance depend on whether it is followed by batch padding ("processed zeros") or by the end of the tensor.
+        # The longest utterance of a shard loses its padding when it was not the longest of the whole batch, and may
+        # differ inside the vocoder's receptive field of its end (< 16 frames); everything before that is bit-identical
+        # (measured: tools/diag_batch_invariance.py, z and z_p are identical in every case).
         ok = len(out) == B
         why = []
+        margin, tail_diffs = 16 * 256, 0
         for i in range(B):
             n = int(ym[i].sum()) * 256
             if out[i].shape[0] != n:
                 why.append(f"utterance {i}: {out[i].shape[0]} samples, expected {n}")
             elif not torch.equal(out[i], o[i, 0, :n]):
-                why.append(f"utterance {i}: max |diff| {float((out[i] - o[i, 0, :n]).abs().max()):.3e}")
+                if torch.equal(out[i][:n - margin], o[i, 0, :n - margin]):
+                    tail_diffs += 1
+                else:
+                    why.append(f"utterance {i}: differs before the last {margin} samples, max |diff| "
+                               f"{float((out[i] - o[i, 0, :n]).abs().max()):.3e}")
+        if tail_diffs > world:
+            why.append(f"{tail_diffs} utterances differ at the tail; at most one per shard can")
         ret["ok"] = bool(ok and not why)
         ret["why"] = "; ".join(why)
     dist.barrier()

@@ -107,5 +107,18 @@ def tc16p_emu_binary(tmp_path_factory):
                                   (96, 128, 3, 2, 3, 520, 64, 32, 2, 2, 0), (40, 96, 7, 3, 2, 700, 32, 16, 3, 0, 1),
                                   (192, 128, 1, 1, 2, 260, 128, 64, 1, 1, 0), (32, 64, 3, 12, 1, 1000, 64, 32, 1, 1, 1)])
 def test_pipelined_conv_kernel_in_emulator(tc16p_emu_binary, case):
-    r = subprocess.run([tc16p_emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=1500)
+    # default role assignment of the harness and of the launcher: all worker warps stage, then drain; one accumulator set.
+    # EMU_TIMEOUT_S: a drain warp legitimately waits for a whole emulated item of MMAs (slow on a loaded machine)
+    r = subprocess.run([tc16p_emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=2400,
+                       env=dict(os.environ, EMU_TIMEOUT_S="900"))
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+# (the two-accumulator-slot experiment, EMU_PINGPONG=1 with dedicated drain warps, is NOT covered: that combination deadlocks
+# intermittently in the emulator and is off by default in the launcher)
+@pytest.mark.parametrize("env", [dict(EMU_PINGPONG="1", EMU_ALLWARPS="1"), dict(EMU_PINGPONG="0", EMU_ALLWARPS="0"), dict(EMU_NTMINOR="0", EMU_NB="2")])
+def test_pipelined_conv_kernel_role_assignments(tc16p_emu_binary, env):
+    """the other role assignments / ring depths of the pipelined kernel on one multi-tile, multi-chunk gate-epilogue case"""
+    r = subprocess.run([tc16p_emu_binary] + [str(v) for v in (96, 128, 3, 2, 2, 520, 64, 32, 2, 2, 0)], capture_output=True, text=True,
+                       timeout=2400, env=dict(os.environ, EMU_TIMEOUT_S="900", **env))
     assert r.returncode == 0, r.stdout + r.stderr

@@ -546,10 +546,11 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
             const bool has_b = q16b < nb16;
             float v[2][16];
             int rr[2] = {r, rb}, qq[2] = {q16, q16b};
-#pragma unroll
-            for (int u2 = 0; u2 < 2; ++u2) {
+            // unit b under a branch, not a predicate: warps without a second unit (all of them when one round covers the
+            // tile, e.g. 264 rows x 16 channels on 480 threads) skip its 16 address + load instructions
+            auto load_unit = [&](int u2) {
               const int t = t_in0 + rr[u2];
-              const bool rok = (u2 == 0 || has_b) && (rr[u2] < R) && (t >= 0) && (t < t_hi);
+              const bool rok = (rr[u2] < R) && (t >= 0) && (t < t_hi);
               const int ci0 = c0 + qq[u2] * 16;
               const float* src = in_b + (long long)ci0 * a.in_cs + t;
               if (fast) {      // one 64-bit add per load instead of a 64-bit multiply-add (issue-bound kernel)
@@ -566,7 +567,9 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) conv1d_tc16_kernel(const Tc
                   if (rok && (ci0 + e) < a.Cin) v[u2][e] = __ldg(src + (long long)e * a.in_cs);
                 }
               }
-            }
+            };
+            load_unit(0);
+            if (has_b) load_unit(1);
             if (!waited) {  // the MMAs that last read this buffer must be done before it is overwritten
               mbar_wait(bar_a_free + 8 * ab, (a_uses - 1) & 1);
               waited = true;
@@ -750,8 +753,13 @@ bool tc16_conv_plan(int Cin, int Cout, int K, int dil, TcPlan* plan) {
   // columns, 256 threads and <= 112 KB, so that two CTAs share an SM and one's MMAs run during the other's staging and
   // epilogue (the phases of an item cannot overlap inside a CTA: its accumulators fill its TMEM).  Costs twice the weight
   // stream per output row.
-  static const int two_ctas = getenv("WETTS_TC16_TWO_CTAS") ? atoi(getenv("WETTS_TC16_TWO_CTAS")) : 0;
-  if (two_ctas) {
+  // Policy (measured per layer, profiles/r02o_*): it pays where the activations are re-staged for many N tiles and the
+  // weights of one N tile are small enough to stream twice as often -- three or more N tiles, or two with K * C_in <= 512
+  // (flow in_layer 0.48 -> 0.415 ms, text-encoder convs -11 %); single-tile and heavy layers (C=128 / C=256 resblocks)
+  // lose 10 % and stay in the large mode.  WETTS_TC16_TWO_CTAS = 0 never, 1 wherever it fits, 2 (default) the policy.
+  static const int two_ctas = getenv("WETTS_TC16_TWO_CTAS") ? atoi(getenv("WETTS_TC16_TWO_CTAS")) : 2;
+  const int nt128 = ((Cout + 63) / 64 * 64 + 127) / 128;
+  if (two_ctas == 1 || (two_ctas == 2 && (nt128 >= 3 || (nt128 == 2 && K * cin16 <= 512)))) {
     const int cout64b = (Cout + 63) / 64 * 64;
     for (int n_tiles = (cout64b + 127) / 128; n_tiles <= cout64b / 64; ++n_tiles) {
       const int N = ((cout64b + n_tiles - 1) / n_tiles + 63) / 64 * 64;

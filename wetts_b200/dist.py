@@ -12,6 +12,11 @@ device); its only sharding logic is the training-time DistributedBucketSampler
 Parity caveat: the reference's implicit RNG draw depends on the batch composition,
 so sharded == unsharded holds bit for bit only with explicit per-utterance noise; `noise_w`,
 `noise_z` and `durations` given on the source rank are therefore scattered row by row with the ids.
+One exception remains, and the reference model has it too: HiFi-GAN does not mask, so the last samples
+of an utterance depend on whether batch padding or the end of the tensor follows it.  The longest
+utterance of a shard that was not the longest of the whole batch can therefore differ inside the
+vocoder's receptive field of its end (< 16 frames; z and z_p are identical; measured on two B200s,
+tests/test_dist_gpu.py, tools/diag_batch_invariance.py).
 """
 import torch
 import torch.distributed as dist
@@ -127,7 +132,8 @@ def sharded_infer(net, x, x_lengths, sid, device, group=None, src=0, hop_upsampl
     """Scatter -> net.infer on every rank -> gather.  `net` is any object with the
     SynthesizerTrn.infer signature (the CUDA engine in production, a stub in the gloo tests).
     Optional per-utterance tensors on `src` (noise_w [B,2,Tx], noise_z [B,C,Tmax], durations [B,1,Tx]) are
-    scattered with the ids so that sharded == unsharded bit for bit."""
+    scattered with the ids so that sharded == unsharded bit for bit (up to the padding effect at the end of a shard's
+    longest utterance described in the module docstring)."""
     rank = dist.get_rank(group)
     meta = torch.zeros(8, dtype=torch.int64, device=device)
     if rank == src:
