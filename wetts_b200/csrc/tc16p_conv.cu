@@ -47,10 +47,13 @@ bool launch_conv1d_tc16p(const ConvArgs& a, cudaStream_t s) {
   p.tmem_cols = pl.tmem_cols; p.G = pl.tmem_cols / (MB * 2 * pl.N);
   if (opt_pp && p.G >= 2) { p.G = p.G / 2; p.acc_slots = 2; }
   p.n_abuf = na; p.n_bbuf = nb;
-  static const int opt_aw = getenv("WETTS_TC16P_ALLWARPS") ? atoi(getenv("WETTS_TC16P_ALLWARPS")) : 2;
+  static const int opt_aw = getenv("WETTS_TC16P_ALLWARPS") ? atoi(getenv("WETTS_TC16P_ALLWARPS")) : 1;
   static const int opt_nt_minor = getenv("WETTS_TC16_NTMINOR") ? atoi(getenv("WETTS_TC16_NTMINOR")) : 1;
   static const int opt_prefetch = getenv("WETTS_TC16_PREFETCH") ? atoi(getenv("WETTS_TC16_PREFETCH")) : 1;
-  p.all_warps = (opt_aw == 2) ? (p.acc_slots == 2 ? 0 : 1) : opt_aw;   // 2 (default): dedicated drain warps when they can overlap the MMAs
+  // 1 (default): all worker warps stage, then drain -- the assignment validated in the emulator.  0: dedicated staging /
+  // drain warps (experiment: intermittent deadlocks in the emulator, none seen on hardware).  2: dedicated when two
+  // accumulator sets let them overlap the MMAs.
+  p.all_warps = (opt_aw == 2) ? (p.acc_slots == 2 ? 0 : 1) : opt_aw;
   p.nt_minor = (opt_nt_minor && pl.n_chunks > 1 && pl.n_tiles > 1) ? 1 : 0;
   p.l2_prefetch = opt_prefetch;
   static const int opt_skip = getenv("WETTS_TC16_DEBUG_SKIP") ? atoi(getenv("WETTS_TC16_DEBUG_SKIP")) : 0;
