@@ -555,7 +555,7 @@ def run_ours(args):
             try:   # the same reference code in eager mode on this GPU (SURVEY.md §8d "reference-on-B200")
                 arm.to(dev)
                 n_e = min(wl["batch"], max(n_cpu, 16))
-                arm.run(min(2, n_e), dev)
+                arm.run(n_e, dev)     # warm-up at the timed shape (cuDNN picks its algorithms per shape on first use)
                 a_e, dt_e, _ = arm.run(n_e, dev)
                 gpu_eager = {"value": a_e / dt_e, "unit": "audio-s/s", "kind": arm.kind + " (PyTorch eager, cuDNN/cuBLAS, fp32)",
                              "sample": f"{n_e} utterances, {dt_e * 1e3:.0f} ms"}
