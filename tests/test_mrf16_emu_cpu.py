@@ -123,3 +123,27 @@ def test_pipelined_conv_kernel_role_assignments(tc16p_emu_binary, env):
     r = subprocess.run([tc16p_emu_binary] + [str(v) for v in (96, 128, 3, 2, 2, 520, 64, 32, 2, 2, 0)], capture_output=True, text=True,
                        timeout=2400, env=dict(os.environ, EMU_TIMEOUT_S="900", **env))
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+# ---- row-block-resident per-layer conv kernel (tc16r_conv_kernel.cuh) in the same emulator
+@pytest.fixture(scope="module")
+def tc16r_emu_binary(tmp_path_factory):
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    out = str(tmp_path_factory.mktemp("emu_tc16r") / "tc16r_emu")
+    subprocess.run([cxx, "-O2", "-std=c++20", "-pthread", "-x", "c++", "-I", EMU, "-I", os.path.join(ROOT, "wetts_b200", "csrc"),
+                    os.path.join(EMU, "tc16r_emu.cpp"), "-o", out], check=True, capture_output=True, text=True)
+    return out
+
+
+# (Cin, Cout, K, dil, B, T, N, KC, grid, epilogue mode, length-aware): 1..4 N tiles through the two TMEM halves, the shapes of
+# a flow in_layer (192 -> 384, k5, gate) and res_skip (1x1, residual), a polyphase upsampler (k2), ragged T, skipped blocks
+@pytest.mark.parametrize("case", [(48, 64, 5, 1, 2, 300, 64, 16, 2, 0, 0), (96, 256, 3, 2, 2, 520, 128, 32, 2, 2, 0),
+                                  (192, 384, 1, 1, 2, 260, 128, 64, 2, 1, 0), (40, 96, 7, 3, 2, 700, 32, 16, 3, 0, 1),
+                                  (64, 256, 3, 1, 2, 500, 64, 32, 3, 1, 1), (192, 384, 5, 1, 2, 400, 128, 16, 2, 2, 0),
+                                  (128, 512, 2, 1, 2, 300, 128, 48, 2, 0, 0)])
+def test_resident_conv_kernel_in_emulator(tc16r_emu_binary, case):
+    r = subprocess.run([tc16r_emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=2400,
+                       env=dict(os.environ, EMU_TIMEOUT_S="600"))
+    assert r.returncode == 0, r.stdout + r.stderr

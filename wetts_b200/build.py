@@ -11,8 +11,8 @@ import sys
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libwetts_b200.so")
-SOURCES = ["engine.cu", "conv_kernels.cu", "misc_kernels.cu", "tc_conv_kernel.cu", "tc16_conv_kernel.cu", "tc16p_conv.cu", "fused_rb.cu", "fused_mrf16.cu", "attn_tc.cu"]
-HEADERS = ["kernels.cuh", "conv_args.h", "tc_epilogue.cuh", "epilogue.cuh", "tc_prims.cuh", "fused_rb_args.h", "fused_rb_kernel.cuh", "fused_mrf16_args.h", "fused_mrf16_kernel.cuh", "attn_tc_kernel.cuh", "tc16p_conv_kernel.cuh", os.path.join("..", "..", "include", "wetts_b200.h")]
+SOURCES = ["engine.cu", "conv_kernels.cu", "misc_kernels.cu", "tc_conv_kernel.cu", "tc16_conv_kernel.cu", "tc16p_conv.cu", "tc16r_conv.cu", "fused_rb.cu", "fused_mrf16.cu", "attn_tc.cu"]
+HEADERS = ["kernels.cuh", "conv_args.h", "tc_epilogue.cuh", "epilogue.cuh", "tc_prims.cuh", "fused_rb_args.h", "fused_rb_kernel.cuh", "fused_mrf16_args.h", "fused_mrf16_kernel.cuh", "attn_tc_kernel.cuh", "tc16p_conv_kernel.cuh", "tc16r_conv_kernel.cuh", os.path.join("..", "..", "include", "wetts_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -48,7 +48,7 @@ static int ensure_fault_word(int device) {
   unsigned int* dptr = nullptr;
   if (cudaHostGetDevicePointer((void**)&dptr, w, 0) != cudaSuccess) return 1;
   return tc_conv_install_fault_word(dptr) | tc16_conv_install_fault_word(dptr) | fused_rb_install_fault_word(dptr) |
-         fused_mrf16_install_fault_word(dptr) | attn_tc_install_fault_word(dptr) | tc16p_install_fault_word(dptr);
+         fused_mrf16_install_fault_word(dptr) | attn_tc_install_fault_word(dptr) | tc16p_install_fault_word(dptr) | tc16r_install_fault_word(dptr);
 }
 // nonzero (and the word cleared) if a device-side pipeline wait timed out since the last check
 static unsigned int take_fault() {

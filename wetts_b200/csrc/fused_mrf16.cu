@@ -109,7 +109,9 @@ static int launch_variant(const FusedMrfArgs& a, int grid, size_t smem, cudaStre
 // CTAs per SM: the accumulators are reused by every conv (4N TMEM columns) and the f16 tiles are half the size of the
 // tf32 ones, so the ResBlock2 kernels fit 3 (C = 32) / 2... CTAs; co-resident CTAs overlap one CTA's SIMT phases with
 // another's MMAs.  WETTS_MRF16_CTAS overrides (experiments).
-static const int g_c64_ctas = getenv("WETTS_MRF16_C64_CTAS") ? atoi(getenv("WETTS_MRF16_C64_CTAS")) : 1;
+// C = 64, ResBlock2: two 256-thread CTAs per SM instead of one 512-thread CTA: -0.9 ms per step in a same-box A/B (two
+// repeats each: 73.35 / 73.57 -> 72.46 / 72.64 ms, profiles/r02t_fused_variants_same_box_ab.txt); WETTS_MRF16_C64_CTAS=1 restores it
+static const int g_c64_ctas = getenv("WETTS_MRF16_C64_CTAS") ? atoi(getenv("WETTS_MRF16_C64_CTAS")) : 2;
 static int ctas_per_sm(int C, int type) {
   static const int forced = getenv("WETTS_MRF16_CTAS") ? atoi(getenv("WETTS_MRF16_CTAS")) : 0;
   if (forced > 0) return forced;

@@ -35,6 +35,10 @@ bool launch_conv1d_tc16p(const ConvArgs& a, cudaStream_t s);
 bool tc16p_enabled();
 void set_tc16p_enabled(bool on);
 int tc16p_install_fault_word(unsigned int* word);
+// row-block-resident variant (tc16r_conv.cu) for layers planned with the two-CTA tiling and several N tiles; false = not taken
+bool launch_conv1d_tc16r(const ConvArgs& a, cudaStream_t s);
+bool tc16r_enabled();
+int tc16r_install_fault_word(unsigned int* word);
 void set_tensor_cores_enabled(bool on);
 bool tensor_cores_enabled();
 

@@ -812,6 +812,7 @@ void launch_pack_conv_tc16(const float* src, void* dst, const int* co_map, const
 }
 
 void launch_conv1d_tc16(const ConvArgs& a, cudaStream_t s) {
+  if (tc16r_enabled() && launch_conv1d_tc16r(a, s)) return;
   if (tc16p_enabled() && launch_conv1d_tc16p(a, s)) return;
   const TcPlan& pl = a.tc16;
   TcConvArgs p;

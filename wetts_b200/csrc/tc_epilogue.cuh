@@ -42,83 +42,96 @@ WETTS_DEVICE void tc_epilogue_prefetch(const ConvArgs& a, int b, int c_lo, int c
   }
 }
 
-// Fused epilogue of one 16-channel slice of one output row, specialised per mode with the switch
-// hoisted out of the element loops: all global loads of the slice are issued before the first store.
-// v[i] already contains bias (+ conditioning).
-WETTS_DEVICE void tc_epilogue_slice_p(const ConvArgs& a, int b, int t, int co0, float* v, float msk) {
+// NE strided loads / stores (channel stride `step` floats): one 64-bit add per element and, for a full slice, no
+// per-element predicate (the kernels around these epilogues are bound by instruction issue).
+template <int NE>
+WETTS_DEVICE void ep_ld_strided(const float* p, long long step, int nval, float (&r)[16]) {
+  if (nval >= NE) {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { r[i] = *p; p += step; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { r[i] = (i < nval) ? *p : 0.f; p += step; }
+  }
+}
+template <int NE>
+WETTS_DEVICE void ep_st_strided(float* p, long long step, int nval, const float (&x)[16]) {
+  if (nval >= NE) {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { *p = x[i]; p += step; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NE; ++i) { if (i < nval) *p = x[i]; p += step; }
+  }
+}
+
+// Fused epilogue of one 16-channel slice of one output row with the mode as a template parameter (branch-free per
+// instantiation).  v[i] already contains bias (+ conditioning).
+template <int MODE>
+WETTS_DEVICE void tc_epilogue_slice_m(const ConvArgs& a, int b, int t, int co0, float* v, float msk) {
   const ConvEpilogue& e = a.ep;
   const size_t Ts = (size_t)a.T;
+  const long long step = (long long)Ts;
   const size_t row = (size_t)b * (size_t)e.out_bs + (size_t)t;
   const int nval = ep_min(16, a.Cout - co0);
-  switch (e.mode) {
+  float x[16], r[16];
+  switch (MODE) {
     case EPI_PLAIN: {
-      float* op = e.out + row + (size_t)co0 * Ts;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float x = v[i];
-        if (e.act == 1) x = fmaxf(x, 0.f);
-        else if (e.act == 2) x = ep_gelu(x);
-        if (e.out_mask) x *= msk;
-        if (i < nval) op[(size_t)i * Ts] = x;
+        x[i] = v[i];
+        if (e.act == 1) x[i] = fmaxf(x[i], 0.f);
+        else if (e.act == 2) x[i] = ep_gelu(x[i]);
+        if (e.out_mask) x[i] *= msk;
       }
+      ep_st_strided<16>(e.out + row + (size_t)co0 * Ts, step, nval, x);
       break;
     }
     case EPI_RESID: {
-      const float* rp = e.resid + row + (size_t)co0 * Ts;
-      float* op = e.out + row + (size_t)co0 * Ts;
-      float r[16];
+      ep_ld_strided<16>(e.resid + row + (size_t)co0 * Ts, step, nval, r);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? rp[(size_t)i * Ts] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nval) op[(size_t)i * Ts] = v[i] + r[i];
+      for (int i = 0; i < 16; ++i) x[i] = v[i] + r[i];
+      ep_st_strided<16>(e.out + row + (size_t)co0 * Ts, step, nval, x);
       break;
     }
     case EPI_MRF: {
-      const float* rp = e.resid + row + (size_t)co0 * Ts;
       float* op = e.out + row + (size_t)co0 * Ts;
-      float r[16], o[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? rp[(size_t)i * Ts] : 0.f;
-      if (e.acc_mode != 0) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = (i < nval) ? op[(size_t)i * Ts] : 0.f;
-      }
+      float o[16];
+      ep_ld_strided<16>(e.resid + row + (size_t)co0 * Ts, step, nval, r);
+      if (e.acc_mode != 0) ep_ld_strided<16>(op, step, nval, o);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        float x = v[i] + r[i];
-        if (e.acc_mode == 1) x = o[i] + x;
-        else if (e.acc_mode == 2) x = (o[i] + x) / e.div;
-        if (i < nval) op[(size_t)i * Ts] = x;
+        x[i] = v[i] + r[i];
+        if (e.acc_mode == 1) x[i] = o[i] + x[i];
+        else if (e.acc_mode == 2) x[i] = (o[i] + x[i]) / e.div;
       }
+      ep_st_strided<16>(op, step, nval, x);
       break;
     }
     case EPI_GATE: {
-      float* op = e.out + row + (size_t)(co0 >> 1) * Ts;
 #pragma unroll
-      for (int i = 0; i < 16; i += 2)
-        if (i < nval) op[(size_t)(i >> 1) * Ts] = ep_gate(v[i], v[i + 1]);
+      for (int i = 0; i < 8; ++i) x[i] = ep_gate(v[2 * i], v[2 * i + 1]);
+      ep_st_strided<8>(e.out + row + (size_t)(co0 >> 1) * Ts, step, (nval + 1) >> 1, x);
       break;
     }
     case EPI_RES_SKIP: {
       if (!e.last && co0 < e.H) {  // residual stream (a 16-slice never straddles H: H % 16 == 0 is checked on the host)
         float* xp = e.x + row + (size_t)co0 * Ts;
-        float r[16];
+        ep_ld_strided<16>(xp, step, nval, r);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? xp[(size_t)i * Ts] : 0.f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < nval) xp[(size_t)i * Ts] = (r[i] + v[i]) * msk;
+        for (int i = 0; i < 16; ++i) x[i] = (r[i] + v[i]) * msk;
+        ep_st_strided<16>(xp, step, nval, x);
       } else {
         float* sp = e.skip + row + (size_t)(e.last ? co0 : co0 - e.H) * Ts;
-        float r[16];
         if (!e.skip_init) {
+          ep_ld_strided<16>(sp, step, nval, r);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? sp[(size_t)i * Ts] : 0.f;
+          for (int i = 0; i < 16; ++i) x[i] = r[i] + v[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[i] = v[i];
         }
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i < nval) sp[(size_t)i * Ts] = e.skip_init ? v[i] : r[i] + v[i];
+        ep_st_strided<16>(sp, step, nval, x);
       }
       break;
     }
@@ -158,13 +171,11 @@ WETTS_DEVICE void tc_epilogue_slice_p(const ConvArgs& a, int b, int t, int co0, 
     }
     case EPI_COUPLING: {
       float* zp = e.out + row + (size_t)(e.z_c0 + co0 * e.z_cstep) * Ts;
-      const long long step = (long long)e.z_cstep * (long long)Ts;
-      float r[16];
+      const long long zstep = (long long)e.z_cstep * (long long)Ts;
+      ep_ld_strided<16>(zp, zstep, nval, r);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = (i < nval) ? zp[(long long)i * step] : 0.f;
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < nval) zp[(long long)i * step] = (r[i] - v[i] * msk) * msk;
+      for (int i = 0; i < 16; ++i) x[i] = (r[i] - v[i] * msk) * msk;
+      ep_st_strided<16>(zp, zstep, nval, x);
       break;
     }
     default:
@@ -172,5 +183,18 @@ WETTS_DEVICE void tc_epilogue_slice_p(const ConvArgs& a, int b, int t, int co0, 
   }
 }
 
+// the same with the mode read at run time (pipelined kernel tc16p)
+WETTS_DEVICE void tc_epilogue_slice_p(const ConvArgs& a, int b, int t, int co0, float* v, float msk) {
+  switch (a.ep.mode) {
+    case EPI_PLAIN: tc_epilogue_slice_m<EPI_PLAIN>(a, b, t, co0, v, msk); break;
+    case EPI_RESID: tc_epilogue_slice_m<EPI_RESID>(a, b, t, co0, v, msk); break;
+    case EPI_MRF: tc_epilogue_slice_m<EPI_MRF>(a, b, t, co0, v, msk); break;
+    case EPI_GATE: tc_epilogue_slice_m<EPI_GATE>(a, b, t, co0, v, msk); break;
+    case EPI_RES_SKIP: tc_epilogue_slice_m<EPI_RES_SKIP>(a, b, t, co0, v, msk); break;
+    case EPI_COUPLING: tc_epilogue_slice_m<EPI_COUPLING>(a, b, t, co0, v, msk); break;
+    case EPI_CONVT: tc_epilogue_slice_m<EPI_CONVT>(a, b, t, co0, v, msk); break;
+    default: break;
+  }
+}
 
 }  // namespace wetts
