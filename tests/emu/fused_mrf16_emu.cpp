@@ -1,7 +1,7 @@
 // CPU check of fused_mrf16_kernel (wetts_b200/csrc/fused_mrf16_kernel.cuh) in the CTA emulator: the kernel source is
 // compiled for the host and compared with a direct fp64 evaluation of ResBlock1 / ResBlock2 x nrb + MRF mean
 // (decoders.py:157-170, :205-214, :72-76).
-//   usage: fused_mrf16_emu type C B T grid [nrb] [ring slots: 4 | 6] [threads] [length-aware: 0 | 1]
+//   usage: fused_mrf16_emu type C B T grid [nrb] [ring slots: 4 | 6] [threads] [length-aware: 0 | 1] [item rows: 128 | 256]
 #define WETTS_EMULATE 1
 #include <math.h>
 
@@ -28,7 +28,7 @@ static void conv_ref(const std::vector<double>& x, std::vector<double>& y, const
     }
 }
 
-template <int C, int THREADS, int NB, int RP, bool TWO>
+template <int C, int THREADS, int NB, int RP, bool TWO, int ITEM = 128>
 static int run(int type, int B, int T, int grid, int nrb, int len_aware) {
   // ResBlock2: v3 recipe kernels 3,5,7 with dilations (1,2),(2,6),(3,12); ResBlock1: v1 recipe 3,7,11 with (1,3,5)
   const int ks2[3] = {3, 5, 7}, d2a[3] = {1, 2, 3}, d2b[3] = {2, 6, 12};
@@ -60,7 +60,7 @@ static int run(int type, int B, int T, int grid, int nrb, int len_aware) {
     Hmax = H > Hmax ? H : Hmax;
   }
   fused_mrf16_finalize_args(a, C);
-  if (RP < 128 + 2 * ((Hmax + 3) & ~3)) { printf("row pitch %d too small for halo %d\n", RP, Hmax); return 64; }
+  if (RP < ITEM + 2 * ((Hmax + 3) & ~3)) { printf("row pitch %d too small for halo %d\n", RP, Hmax); return 64; }
   if ((size_t)a.nq * fused_mrf16_chunk_bytes(C) != packed_halfs * 2) { printf("chunk accounting mismatch\n"); return 1; }
   if (NB == 6 && a.nq % 6 != 0) { printf("6-slot ring needs nq %% 6 == 0 (nq = %d)\n", a.nq); return 64; }
   if (fused_mrf16_smem_bytes(C, NB, RP, TWO ? 2 : 1) > emu::kSmemBytes) { printf("smem over budget\n"); return 1; }
@@ -85,7 +85,7 @@ static int run(int type, int B, int T, int grid, int nrb, int len_aware) {
   a.smem_off = emu::kSmemBase;
   // length-aware: utterance b computes only its first tiles (lengths 60 %, 100 %, 35 %, ... of T); the rest stays -777
   std::vector<int> prefix(B + 1, 0), ntile(B);
-  const int n_tt = (T + 127) / 128;
+  const int n_tt = (T + ITEM - 1) / ITEM;
   for (int b = 0; b < B; ++b) {
     const int pct[4] = {60, 100, 35, 80};
     ntile[b] = len_aware ? std::max(1, (n_tt * pct[b & 3] + 99) / 100) : n_tt;
@@ -93,11 +93,11 @@ static int run(int type, int B, int T, int grid, int nrb, int len_aware) {
   }
   std::vector<int2_t> item_map;
   for (int b = 0; b < B; ++b)
-    for (int i = 0; i < ntile[b]; ++i) item_map.push_back(int2_t{b, i * 128});
+    for (int i = 0; i < ntile[b]; ++i) item_map.push_back(int2_t{b, i * ITEM});
   const int n_items_host = (int)item_map.size();
   if (len_aware) { a.item_map = item_map.data(); a.n_items_dev = &n_items_host; }
   unsigned long long n_mma = 0;
-  emu::launch(fused_mrf16_kernel<C, THREADS, 1, NB, RP, TWO>, a, grid, THREADS, &n_mma);
+  emu::launch(fused_mrf16_kernel<C, THREADS, 1, NB, RP, TWO, false, ITEM>, a, grid, THREADS, &n_mma);
 
   // reference
   double max_err = 0, sq = 0;
@@ -122,7 +122,7 @@ static int run(int type, int B, int T, int grid, int nrb, int len_aware) {
       }
       for (size_t i = 0; i < acc.size(); ++i) acc[i] += cur[i];
     }
-    const int t_done = std::min(T, ntile[b] * 128);
+    const int t_done = std::min(T, ntile[b] * ITEM);
     for (int c = 0; c < C; ++c)
       for (int t = 0; t < T; ++t) {
         const size_t i = (size_t)c * T + t;
@@ -136,8 +136,8 @@ static int run(int type, int B, int T, int grid, int nrb, int len_aware) {
       }
   }
   const double rms = sqrt(sq / (double)cnt);
-  printf("type=%d C=%d thr=%d ring=%d RP=%d B=%d T=%d grid=%d nrb=%d la=%d: mma=%llu max_err=%.3e rms=%.3e rel=%.3e untouched=%d\n", type, C,
-         THREADS, NB, RP, B, T, grid, nrb, len_aware, n_mma, max_err, rms, max_err / rms, untouched_ok);
+  printf("type=%d C=%d thr=%d ring=%d RP=%d item=%d B=%d T=%d grid=%d nrb=%d la=%d: mma=%llu max_err=%.3e rms=%.3e rel=%.3e untouched=%d\n", type, C,
+         THREADS, NB, RP, ITEM, B, T, grid, nrb, len_aware, n_mma, max_err, rms, max_err / rms, untouched_ok);
   free(packed);
   return (max_err / rms < 2e-5 && untouched_ok) ? 0 : 2;
 }
@@ -149,7 +149,18 @@ int main(int argc, char** argv) {
   const int ring = argc > 7 ? atoi(argv[7]) : 4;
   const int thr = argc > 8 ? atoi(argv[8]) : (C == 32 ? 256 : 512);
   const int la = argc > 9 ? atoi(argv[9]) : 0;
+  const int item = argc > 10 ? atoi(argv[10]) : 128;
 #define RUN(CC, TH, NBB, RPP, TW) return run<CC, TH, NBB, RPP, TW>(type, B, T, grid, nrb, la)
+#define RUN256(CC, TH, NBB, RPP, TW) return run<CC, TH, NBB, RPP, TW, 256>(type, B, T, grid, nrb, la)
+  if (item == 256) {
+    // 256-sample work items (three M blocks per conv, two per resblock output)
+    if (type == 2 && C == 32 && thr == 256 && ring == 6) RUN256(32, 256, 6, 353, false);
+    if (type == 2 && C == 32 && thr == 256 && ring == 4) RUN256(32, 256, 4, 353, false);
+    if (type == 2 && C == 64 && thr == 512 && ring == 6) RUN256(64, 512, 6, 353, false);
+    if (type == 2 && C == 64 && thr == 256 && ring == 6) RUN256(64, 256, 6, 353, false);
+    if (type == 1 && C == 32 && thr == 256 && ring == 6) RUN256(32, 256, 6, 377, true);
+    return 64;
+  }
   if (type == 2) {
     if (C == 32 && thr == 256 && ring == 4) RUN(32, 256, 4, 225, false);
     if (C == 32 && thr == 256 && ring == 6) RUN(32, 256, 6, 225, false);

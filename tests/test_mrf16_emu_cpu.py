@@ -28,12 +28,15 @@ def emu_binary(tmp_path_factory):
     return _build(str(tmp_path_factory.mktemp("emu16") / "fused_mrf16_emu"), os.path.join(ROOT, "wetts_b200", "csrc"))
 
 
-# (type, C, B, T, grid, nrb, ring, threads, length-aware): ResBlock2 (v3) and ResBlock1 (v1) stages, both widths, both
+# (type, C, B, T, grid, nrb, ring, threads, length-aware[, item rows]): ResBlock2 (v3) and ResBlock1 (v1) stages, both widths, both
 # ring sizes, ragged last tile, single short tile, more CTAs than items, 1-3 resblocks, the length-aware item list
 CASES = [(2, 32, 2, 300, 2, 3, 4, 256, 0), (2, 32, 1, 76, 1, 3, 6, 256, 0), (2, 32, 2, 256, 5, 1, 6, 256, 0),
          (2, 64, 2, 300, 2, 3, 6, 512, 0), (2, 64, 3, 320, 4, 2, 4, 512, 0), (2, 32, 4, 1000, 3, 3, 6, 256, 1),
          (1, 32, 2, 300, 2, 3, 6, 256, 0), (1, 32, 1, 76, 1, 3, 4, 256, 0), (1, 64, 2, 300, 2, 3, 6, 512, 0),
-         (1, 32, 4, 700, 3, 3, 6, 256, 1)]
+         (1, 32, 4, 700, 3, 3, 6, 256, 1),
+         # 256-sample work items (ITEM = 256: three M blocks per conv, two per resblock output, two prefetched staging units)
+         (2, 32, 2, 300, 2, 3, 6, 256, 0, 256), (2, 32, 1, 76, 1, 3, 6, 256, 0, 256), (2, 32, 4, 1000, 3, 3, 6, 256, 1, 256),
+         (2, 64, 2, 600, 2, 3, 6, 512, 0, 256), (1, 32, 2, 600, 2, 3, 6, 256, 0, 256), (2, 32, 2, 512, 5, 1, 6, 256, 0, 256)]
 
 
 @pytest.mark.parametrize("case", CASES)

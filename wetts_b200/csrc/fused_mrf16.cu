@@ -23,16 +23,16 @@ __global__ void fused_mrf16_pack_kernel(const float* __restrict__ src, uint16_t*
   }
 }
 
-// Work-item list of the length-aware mode: utterance b contributes tiles(b) = ceil(min(T, (len[b] + margin) * rate) / 128)
-// items (at least one), in (b, tile) order.  One block: a serial prefix over B (a few thousand at most), then every
+// Work-item list of the length-aware mode: utterance b contributes tiles(b) = ceil(min(T, (len[b] + margin) * rate) / item)
+// items of `item` output samples (at least one), in (b, tile) order.  One block: a serial prefix over B (a few thousand at most), then every
 // thread fills the segments of its utterances.
-__global__ void mrf_item_map_kernel(const long long* __restrict__ lengths, int B, int T, int rate, int margin,
+__global__ void mrf_item_map_kernel(const long long* __restrict__ lengths, int B, int T, int rate, int margin, int item,
                                     int2_t* __restrict__ item_map, int* __restrict__ n_items, int* __restrict__ prefix) {
   auto tiles = [&](int b) {
     long long n = (lengths[b] + margin) * (long long)rate;
     if (n > T) n = T;
     if (n < 1) n = 1;
-    return (int)((n + 127) / 128);
+    return (int)((n + item - 1) / item);
   };
   if (threadIdx.x == 0) {
     int acc = 0;
@@ -43,7 +43,7 @@ __global__ void mrf_item_map_kernel(const long long* __restrict__ lengths, int B
   __syncthreads();
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const int first = prefix[b], n = prefix[b + 1] - first;
-    for (int i = 0; i < n; ++i) item_map[first + i] = int2_t{b, i * 128};
+    for (int i = 0; i < n; ++i) item_map[first + i] = int2_t{b, i * item};
   }
 }
 
@@ -85,20 +85,35 @@ void launch_fused_mrf16_pack(const float* w_folded, void* dst, int C, int K, cud
 size_t mrf_item_map_bytes(int B, int T) {
   return sizeof(int2_t) * (size_t)B * ((size_t)(T + 127) / 128) + sizeof(int) * ((size_t)B + 2) + 64;
 }
-void launch_mrf_item_map(const long long* lengths, int B, int T, int rate, int margin, void* scratch, const int2_t** item_map,
-                         const int** n_items_dev, cudaStream_t s) {
+void launch_mrf_item_map(const long long* lengths, int B, int T, int rate, int margin, int item_rows, void* scratch,
+                         const int2_t** item_map, const int** n_items_dev, cudaStream_t s) {
   int2_t* map = reinterpret_cast<int2_t*>(scratch);
   int* n_items = reinterpret_cast<int*>(map + (size_t)B * ((size_t)(T + 127) / 128));
   int* prefix = n_items + 1;
-  mrf_item_map_kernel<<<1, 256, 0, s>>>(lengths, B, T, rate, margin, map, n_items, prefix);
+  mrf_item_map_kernel<<<1, 256, 0, s>>>(lengths, B, T, rate, margin, item_rows, map, n_items, prefix);
   count_launch();
   *item_map = map;
   *n_items_dev = n_items;
 }
 
-template <int C, int THREADS, int MINB, int NB, int RP, bool TWO, bool PROFILE>
+// Output samples per work item (fused_mrf16_kernel's ITEM).  256-sample items amortise the halo (5 instead of 6 M blocks
+// per 256 samples of a ResBlock2 conv pair, 13 % fewer staged rows) at the price of three accumulator blocks in TMEM
+// (C = 32: 256 columns -> two CTAs per SM instead of three; C = 64: 512 columns -> one CTA per SM).
+// WETTS_MRF16_ITEM_C32 / _C64 / _RB1 = 128 | 256 override per kernel family (RB1: ResBlock1, C = 32 only).
+int fused_mrf16_item_rows(int C, int type) {
+  static const int c32 = getenv("WETTS_MRF16_ITEM_C32") ? atoi(getenv("WETTS_MRF16_ITEM_C32")) : 128;
+  static const int c64 = getenv("WETTS_MRF16_ITEM_C64") ? atoi(getenv("WETTS_MRF16_ITEM_C64")) : 128;
+  static const int rb1 = getenv("WETTS_MRF16_ITEM_RB1") ? atoi(getenv("WETTS_MRF16_ITEM_RB1")) : 128;
+  if (type == 2 && C == 32) return c32 == 256 ? 256 : 128;
+  if (type == 2 && C == 64) return c64 == 256 ? 256 : 128;
+  if (type == 1 && C == 32) return rb1 == 256 ? 256 : 128;
+  return 128;
+}
+static int tile_pitch(int type, int item) { return item == 256 ? (type == 1 ? 377 : 353) : (type == 1 ? 249 : 225); }
+
+template <int C, int THREADS, int MINB, int NB, int RP, bool TWO, bool PROFILE, int ITEM = 128>
 static int launch_variant(const FusedMrfArgs& a, int grid, size_t smem, cudaStream_t s) {
-  auto kern = fused_mrf16_kernel<C, THREADS, MINB, NB, RP, TWO, PROFILE>;
+  auto kern = fused_mrf16_kernel<C, THREADS, MINB, NB, RP, TWO, PROFILE, ITEM>;
   static DynSmemAttr attr;
   if (attr.ensure((const void*)kern, smem) != cudaSuccess) return 1;
   kern<<<grid, THREADS, smem, s>>>(a);
@@ -121,8 +136,15 @@ static int ctas_per_sm(int C, int type) {
 }
 
 template <bool PROFILE>
-static int launch_any(int C, int type, int ring, int per_sm, const FusedMrfArgs& a, int grid, size_t smem, cudaStream_t s) {
+static int launch_any(int C, int type, int ring, int per_sm, int item, const FusedMrfArgs& a, int grid, size_t smem, cudaStream_t s) {
 #define V(CC, TH, MB, NBB, RPP, TW) launch_variant<CC, TH, MB, NBB, RPP, TW, PROFILE>(a, grid, smem, s)
+#define V256(CC, TH, MB, NBB, RPP, TW) launch_variant<CC, TH, MB, NBB, RPP, TW, PROFILE, 256>(a, grid, smem, s)
+  if (item == 256) {
+    if (type == 2 && C == 32) return ring == 6 ? V256(32, 256, 2, 6, 353, false) : V256(32, 256, 2, 4, 353, false);
+    if (type == 2 && C == 64) return ring == 6 ? V256(64, 512, 1, 6, 353, false) : V256(64, 512, 1, 4, 353, false);
+    if (type == 1 && C == 32) return ring == 6 ? V256(32, 256, 1, 6, 377, true) : V256(32, 256, 1, 4, 377, true);
+    return 1;
+  }
   if (type == 2 && C == 32) {
     if (per_sm >= 3) return ring == 6 ? V(32, 256, 3, 6, 225, false) : V(32, 256, 3, 4, 225, false);
     return ring == 6 ? V(32, 256, 2, 6, 225, false) : V(32, 256, 2, 4, 225, false);
@@ -133,10 +155,11 @@ static int launch_any(int C, int type, int ring, int per_sm, const FusedMrfArgs&
   if (type == 1 && C == 32) return ring == 6 ? V(32, 256, 2, 6, 249, true) : V(32, 256, 2, 4, 249, true);
   if (type == 1 && C == 64) return ring == 6 ? V(64, 512, 1, 6, 249, true) : V(64, 512, 1, 4, 249, true);
 #undef V
+#undef V256
   return 1;
 }
 
-static int launch_profiled(int C, int type, int ring, int per_sm, FusedMrfArgs a, int grid, size_t smem, long long items,
+static int launch_profiled(int C, int type, int ring, int per_sm, int item, FusedMrfArgs a, int grid, size_t smem, long long items,
                            cudaStream_t s) {
   static const char* names[kMrfProfPhases] = {"stage", "sync", "conv issue|prefetch", "acc wait", "epilogue", "sync", "out",
                                               "[full-wait]", "loop", "-", "-", "-"};
@@ -145,14 +168,14 @@ static int launch_profiled(int C, int type, int ring, int per_sm, FusedMrfArgs a
   if (cudaMalloc(&d, n * sizeof(long long)) != cudaSuccess) return 1;
   cudaMemsetAsync(d, 0, n * sizeof(long long), s);
   a.prof = d;
-  if (launch_any<true>(C, type, ring, per_sm, a, grid, smem, s)) return 1;
+  if (launch_any<true>(C, type, ring, per_sm, item, a, grid, smem, s)) return 1;
   if (cudaStreamSynchronize(s) != cudaSuccess) return 1;
   std::vector<long long> h(n);
   cudaMemcpy(h.data(), d, n * sizeof(long long), cudaMemcpyDeviceToHost);
   cudaFree(d);
   const double per_cta_items = (double)items / grid;
-  fprintf(stderr, "[fused_mrf16 profile] type=%d C=%d ring=%d ctas/sm=%d B=%d T=%d grid=%d items/CTA=%.1f  (cycles per item, mean over CTAs)\n",
-          type, C, ring, per_sm, a.B, a.T, grid, per_cta_items);
+  fprintf(stderr, "[fused_mrf16 profile] type=%d C=%d ring=%d ctas/sm=%d item=%d B=%d T=%d grid=%d items/CTA=%.1f  (cycles per item, mean over CTAs)\n",
+          type, C, ring, per_sm, item, a.B, a.T, grid, per_cta_items);
   for (int who = 0; who < 2; ++who) {
     double tot = 0;
     fprintf(stderr, "  %s:", who ? "thread 32 (producer warp)" : "thread 0 (MMA issuer)   ");
@@ -176,18 +199,21 @@ int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
   if (n_sm <= 0) return 1;
   const char* force = getenv("WETTS_FUSED_RB_RING");
   int ring = force ? atoi(force) : fused_mrf16_ring_slots(a.nq);
-  if (ring == 6 && fused_mrf16_smem_bytes(C, 6, (a.type == 1) ? 249 : 225, a.type == 1 ? 2 : 1) > 227 * 1024) ring = 4;
+  const int item = fused_mrf16_item_rows(C, a.type);
+  const int rp = tile_pitch(a.type, item);
+  if (ring == 6 && fused_mrf16_smem_bytes(C, 6, rp, a.type == 1 ? 2 : 1) > 227 * 1024) ring = 4;
   if (ring != 4 && !(ring == 6 && a.nq % 6 == 0)) return 1;
-  const int rp = (a.type == 1) ? 249 : 225;
   const size_t smem = fused_mrf16_smem_bytes(C, ring, rp, a.type == 1 ? 2 : 1);
-  const long long items = (long long)a.B * ((a.T + 127) / 128);   // upper bound in the length-aware mode
-  const int per_sm = ctas_per_sm(C, a.type);
+  if (smem > 227 * 1024) return 1;
+  const long long items = (long long)a.B * ((a.T + item - 1) / item);   // upper bound in the length-aware mode
+  // 256-sample items: three accumulator blocks -> 256 (C = 32) / 512 (C = 64) TMEM columns per CTA
+  const int per_sm = item == 256 ? ((C == 32 && a.type == 2) ? 2 : 1) : ctas_per_sm(C, a.type);
   static const int stagger = getenv("WETTS_MRF16_STAGGER") ? atoi(getenv("WETTS_MRF16_STAGGER")) : 0;
   a.stagger = per_sm > 1 ? stagger : 0;
   a.n_sm = n_sm;
   const int grid = (int)(items < (long long)per_sm * n_sm ? items : (long long)per_sm * n_sm);
-  if (getenv("WETTS_FUSED_RB_PROFILE")) return launch_profiled(C, a.type, ring, per_sm, a, grid, smem, items, s);
-  return launch_any<false>(C, a.type, ring, per_sm, a, grid, smem, s);
+  if (getenv("WETTS_FUSED_RB_PROFILE")) return launch_profiled(C, a.type, ring, per_sm, item, a, grid, smem, items, s);
+  return launch_any<false>(C, a.type, ring, per_sm, item, a, grid, smem, s);
 }
 
 int fused_mrf16_install_fault_word(unsigned int* word) { return tc::install_fault_word_tu(word) == cudaSuccess ? 0 : 1; }

@@ -5,7 +5,9 @@
 //   ResBlock1 (decoders.py:157-170):  for d in (d0, d1, d2):  x = conv_{k,1}(lrelu(conv_{k,d}(lrelu x))) + x
 //   MRF mean (decoders.py:72-76).
 //
-// One launch per generator stage.  Work item = (utterance b, 128 output samples).  For resblock j with total halo
+// One launch per generator stage.  Work item = (utterance b, ITEM output samples), ITEM = 128 or 256 (a 256-sample item
+// amortises the halo: 5 instead of 6 M blocks per 256 samples of a ResBlock2 pair, 13 % fewer staged rows; below,
+// "128" stands for ITEM where the text describes the item).  For resblock j with total halo
 // H = sum of the conv halos, Hp = H rounded up to 4, dl = Hp - H, the CTA stages R = 128 + 2Hp input rows of lrelu(x)
 // as the tcgen05 A operand (M = time rows, K = channels, no-swizzle K-major canonical layout):
 //     element (row r, channel c) at tile + (c/8)*RP*16 + r*16 + (c%8)*2      (fp16; hi tile, then the lo' tile)
@@ -41,16 +43,21 @@
 
 namespace wetts {
 
-template <int C, int THREADS, int MINB, int NB, int RP, bool TWO_TILES, bool PROFILE = false>
+template <int C, int THREADS, int MINB, int NB, int RP, bool TWO_TILES, bool PROFILE = false, int ITEM = 128>
 WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const FusedMrfArgs p) {
   using namespace tc;
   static_assert(C == 32 || C == 64 || C == 128, "channel count");
   static_assert(NB == 4 || NB == 6, "ring size");
   static_assert((RP & 1) == 1 && RP >= 225, "odd row pitch");
+  static_assert(ITEM == 128 || ITEM == 256, "output samples per work item");
+  constexpr int OBLK = ITEM / 128;                              // M blocks of the last conv of a resblock (its output rows)
+  constexpr int MBLK = OBLK + 1;                                // M blocks of any other conv (output + remaining halo <= 128 rows more)
   constexpr int N = C;
   constexpr int KH = C / 32;
   constexpr uint32_t CHUNK_BYTES = 4u * 2u * N * 16u;          // [4 k-groups][hi | lo' : 2N rows][8 halfs]
-  constexpr uint32_t TMEM_COLS = 4u * N;                        // two accumulator blocks x [hi*hi | small terms]
+  // MBLK accumulator blocks x [hi*hi | small terms], rounded up to a power of two (TMEM allocation granularity)
+  constexpr uint32_t TMEM_COLS = (MBLK * 2u * N <= 128u) ? 128u : ((MBLK * 2u * N <= 256u) ? 256u : 512u);
+  static_assert(MBLK * 2 * N <= 512, "accumulator blocks exceed TMEM");
   constexpr int CG8 = C / 8;                                    // 8-channel groups of the activation tile
   constexpr int LOG_CG8 = (CG8 == 4) ? 2 : (CG8 == 8 ? 3 : 4);
   constexpr int NWARP = THREADS / 32, GRPS = NWARP / 4;         // warps sharing a TMEM lane quarter split the columns
@@ -63,8 +70,10 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   constexpr int STHREADS = THREADS - 32 * SW0;
   // one staging unit per thread: its 8 loads are prefetched into registers during the previous MMA phase; more units
   // than threads (C = 64 with 256 threads): NU units per thread, loaded and stored inside the staging phase
-  constexpr bool PREFETCH = (UNITS <= STHREADS);
+  // (256-sample items: two units per thread are prefetched)
   constexpr int NU = (UNITS + STHREADS - 1) / STHREADS;
+  constexpr bool PREFETCH = (NU == 1) || (ITEM > 128 && NU == 2);
+  constexpr int NPF = PREFETCH ? NU : 1;
   constexpr uint32_t A_HALF = (uint32_t)CG8 * RP * 16u;         // bytes of the hi (or lo') tile
   constexpr uint32_t TILE_BYTES = 2u * A_HALF;
   constexpr int NBIAS = kMrfMaxRb * kMrfMaxConv;
@@ -102,7 +111,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   const uint32_t tmem_base = uniform_bits(tmem_raw, 5, 9);
   if (tmem_base != tmem_raw) trap_now();
 
-  const int n_ttiles = (T + 127) / 128;
+  const int n_ttiles = (T + ITEM - 1) / ITEM;
   const int n_items = p.item_map ? ldg_i32(p.n_items_dev) : p.B * n_ttiles;
   const int my_items = (WETTS_BID < n_items) ? (n_items - WETTS_BID + WETTS_NBLK - 1) / WETTS_NBLK : 0;
   const long long bs = (long long)C * T;
@@ -116,7 +125,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
       t0 = ldg_i32(&p.item_map[item].y);
     } else {
       b = item / n_ttiles;
-      t0 = (item - b * n_ttiles) * 128;
+      t0 = (item - b * n_ttiles) * ITEM;
     }
   };
   auto halo_of = [&](int j) {
@@ -128,7 +137,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   // ---------------------------------------------------------------- activation prefetch / staging
   // unit u = (8-channel group cg = u % CG8, row quad q = u / CG8): eight 16 B loads (8 channels x 4 consecutive
   // samples), transposed in registers into four (row, 8-channel) 16 B stores per hi / lo' tile
-  float4 pf[8];
+  float4 pf[NPF][8];
   const int su = tid - 32 * SW0;                       // staging unit of this thread (negative: not a staging thread)
   auto prefetch = [&](int item, int j) {
     if (!PREFETCH) return;
@@ -136,13 +145,17 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
     int b, t0;
     decode(item, b, t0);
     const int Hp = (halo_of(j) + 3) & ~3;
-    const int Q = (128 + 2 * Hp) >> 2;
-    const int cg = su & (CG8 - 1), q = su >> LOG_CG8;
-    const int t = t0 - Hp + 4 * q;
-    const bool ok = (q < Q) && (t >= 0) && (t < T);     // T % 4 == 0 (host-checked): a quad is all in or all out
-    const float* src = p.in + (long long)b * bs + (long long)(8 * cg) * T + t;
+    const int Q = (ITEM + 2 * Hp) >> 2;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) pf[e] = ok ? ldg4(src + (long long)e * T) : float4{0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < NPF; ++i) {
+      const int u = su + i * STHREADS;
+      const int cg = u & (CG8 - 1), q = u >> LOG_CG8;
+      const int t = t0 - Hp + 4 * q;
+      const bool ok = (u < UNITS) && (q < Q) && (t >= 0) && (t < T);     // T % 4 == 0 (host-checked): a quad is all in or all out
+      const float* src = p.in + (long long)b * bs + (long long)(8 * cg) * T + t;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pf[i][e] = ok ? ldg4(src + (long long)e * T) : float4{0.f, 0.f, 0.f, 0.f};
+    }
   };
   auto lrelu = [&](float x) { return fmaxf(x, x * slope); };                  // 0 < slope < 1
   auto inv_lrelu = [&](float y) { return fminf(y, y * inv_slope); };
@@ -157,29 +170,33 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
     *reinterpret_cast<uint4*>(dst) = hi;
     *reinterpret_cast<uint4*>(dst + A_HALF) = lo;
   };
-  auto store_unit = [&](int cg, int q) {
+  auto store_unit = [&](const float4 (&pu)[8], int cg, int q) {
     float y[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = lrelu(pf[e].x);
+    for (int e = 0; e < 8; ++e) y[e] = lrelu(pu[e].x);
     split_store8(Xt, cg, 4 * q + 0, y);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = lrelu(pf[e].y);
+    for (int e = 0; e < 8; ++e) y[e] = lrelu(pu[e].y);
     split_store8(Xt, cg, 4 * q + 1, y);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = lrelu(pf[e].z);
+    for (int e = 0; e < 8; ++e) y[e] = lrelu(pu[e].z);
     split_store8(Xt, cg, 4 * q + 2, y);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) y[e] = lrelu(pf[e].w);
+    for (int e = 0; e < 8; ++e) y[e] = lrelu(pu[e].w);
     split_store8(Xt, cg, 4 * q + 3, y);
   };
   auto stage = [&](int item, int j) {
     if (su < 0) return;
     const int Hp = (halo_of(j) + 3) & ~3;
-    const int Q = (128 + 2 * Hp) >> 2;
+    const int Q = (ITEM + 2 * Hp) >> 2;
     if (PREFETCH) {
       if (su >= UNITS) return;
-      const int cg = su & (CG8 - 1), q = su >> LOG_CG8;
-      if (q < Q) store_unit(cg, q);
+#pragma unroll
+      for (int i = 0; i < NPF; ++i) {
+        const int u = su + i * STHREADS;
+        const int cg = u & (CG8 - 1), q = u >> LOG_CG8;
+        if (u < UNITS && q < Q) store_unit(pf[i], cg, q);
+      }
     } else {
       int b, t0;
       decode(item, b, t0);
@@ -192,8 +209,8 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
           const bool ok = (t >= 0) && (t < T);
           const float* src = p.in + (long long)b * bs + (long long)(8 * cg) * T + t;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) pf[e] = ok ? ldg4(src + (long long)e * T) : float4{0.f, 0.f, 0.f, 0.f};
-          store_unit(cg, q);
+          for (int e = 0; e < 8; ++e) pf[0][e] = ok ? ldg4(src + (long long)e * T) : float4{0.f, 0.f, 0.f, 0.f};
+          store_unit(pf[0], cg, q);
         }
       }
     }
@@ -267,12 +284,13 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   constexpr uint32_t A_LO_DELTA = A_HALF >> 4, T_DELTA = TILE_BYTES >> 4;
 
   // One conv on the tensor pipe (warp 0): for every tap and 32-channel slice, multiply the weight chunk with `nblk`
-  // 128-row blocks of the source tile (block m starts at row row0 + m*row_step + tap*dil).
+  // 128-row blocks of the source tile (block m starts at row row0 + m*128 + tap*dil; the last block at row0 + n_out - 128,
+  // so it ends with the conv's last output row and may overlap its predecessor).
   // ring_base = low bits of this item's first chunk number: only slot and phase parity matter to the consumer.
   // Issue-path hygiene (SASS-verified: unpredicated UTCHMMA fed by UIADD3/UMOV only): all scalars here derive from kernel
   // parameters and loop counters; the epilogue loops use structured ifs only (no `continue` under a thread-dependent
   // condition); no thread-dependent branch to a trap after the prologue.
-  auto run_conv = [&](uint32_t ring_base, uint32_t qbase, int k, int dil, int nblk, int row0, int row_step, uint32_t tile_delta) {
+  auto run_conv = [&](uint32_t ring_base, uint32_t qbase, int k, int dil, int nblk, int row0, int n_out, uint32_t tile_delta) {
     for (int tap = 0; tap < k; ++tap) {
       for (int kh = 0; kh < KH; ++kh) {
         const uint32_t q = qbase + (uint32_t)(tap * KH + kh);
@@ -294,7 +312,9 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
         const uint32_t b0 = blo0 + slot * (CHUNK_BYTES >> 4);
         const uint32_t first = (tap == 0 && kh == 0) ? 0u : 1u;   // 0: overwrite the accumulators
         for (int m = 0; m < nblk; ++m) {
-          const uint32_t a0 = alo0 + tile_delta + (uint32_t)((kh * 4) * RP + row0 + m * row_step + tap * dil);
+          // (ITEM == 128: at most two blocks, written as in the 128-sample kernel this generalises -- same code as before)
+          const int m_row = (ITEM == 128) ? m * (n_out - 128) : ((m == nblk - 1) ? n_out - 128 : m * 128);
+          const uint32_t a0 = alo0 + tile_delta + (uint32_t)((kh * 4) * RP + row0 + m_row + tap * dil);
           const uint32_t d_tmem = tmem_base + (uint32_t)(m * 2 * N);
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
@@ -331,16 +351,18 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
     const int item = WETTS_BID + it * WETTS_NBLK;
     int b, t0;
     decode(item, b, t0);
-    float racc[SL][16];
+    float racc[OBLK][SL][16];
 #pragma unroll
-    for (int s = 0; s < SL; ++s)
+    for (int o = 0; o < OBLK; ++o)
 #pragma unroll
-      for (int i = 0; i < 16; ++i) racc[s][i] = 0.f;
+      for (int s = 0; s < SL; ++s)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) racc[o][s][i] = 0.f;
 
     for (int j = 0; j < nrb; ++j) {
       const int k = p.k[j];
       const int H = halo_of(j), Hp = (H + 3) & ~3;
-      const int R = 128 + 2 * Hp;
+      const int R = ITEM + 2 * Hp;
       const int next_item = (j + 1 < nrb) ? item : ((it + 1 < my_items) ? item + WETTS_NBLK : -1);
       const int next_j = (j + 1 < nrb) ? j + 1 : 0;
 
@@ -357,13 +379,14 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
       for (int c = 0; c < nconv; ++c) {
         const int d = p.dil[j][c], h = d * (k - 1) / 2;
         const int lo_out = lo + h, n_out = R - 2 * lo_out;
-        const int nblk = (n_out > 128) ? 2 : 1, step = n_out - 128;
+        const int nblk = (ITEM == 128) ? ((n_out > 128) ? 2 : 1) : ((n_out + 127) >> 7);   // <= MBLK (host-checked); the last conv: exactly OBLK
+        const int ov = 128 * nblk - n_out;               // rows the last block shares with its predecessor
         const bool last = (c == nconv - 1);
         const bool inner = TWO_TILES && ((c & 1) == 0);      // ResBlock1's first conv of a pair: X -> T, no residual
         const bool from_t = TWO_TILES && ((c & 1) == 1);
         if (warp == 0) {
           const uint32_t ring_base = (NB == 4) ? (((uint32_t)it * nq) & 7u) : (((uint32_t)it * (uint32_t)p.nq_ring) & 1u);
-          run_conv(ring_base, (uint32_t)p.qoff[j][c], k, d, nblk, lo, step, from_t ? T_DELTA : 0u);
+          run_conv(ring_base, (uint32_t)p.qoff[j][c], k, d, nblk, lo, n_out, from_t ? T_DELTA : 0u);
         } else if (warp == 1) {
           produce_range((uint32_t)it, (uint32_t)p.qoff[j][c], (uint32_t)(k * KH));
         }
@@ -380,10 +403,11 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
         // joins at a divergent branch makes the loop exit -- and every MMA operand after it -- "divergent" for ptxas.
 #pragma unroll 1
         for (int mb = 0; mb < nblk; ++mb) {
-          const bool quarter_has_rows = (mb == 0) || (32 * q4 + 31 >= 128 - step);      // warp-uniform
+          const bool tail = (ITEM == 128) ? (mb != 0) : ((mb > 0) && (mb == nblk - 1));   // the block that may overlap
+          const bool quarter_has_rows = !tail || (32 * q4 + 31 >= ov);                  // warp-uniform
           if (quarter_has_rows) {
-            const bool active = (mb == 0) || (row_i >= 128 - step);
-            const int r = lo_out + (mb ? step : 0) + row_i;
+            const bool active = !tail || (row_i >= ov);
+            const int r = lo_out + (tail ? n_out - 128 : 128 * mb) + row_i;
             const int t = t0 - Hp + r;
             const bool inside = (t >= 0) && (t < T);
 #pragma unroll
@@ -408,8 +432,13 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
                     for (int e = 0; e < 8; ++e) val[e] += x[e];
                   }
                   if (last) {
+                    // (the last conv has exactly OBLK blocks, none overlapping: mb indexes the register accumulator)
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) racc[s][8 * g8 + e] += val[e];
+                    for (int o = 0; o < OBLK; ++o)
+                      if (OBLK == 1 || o == mb) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) racc[o][s][8 * g8 + e] += val[e];
+                      }
                   } else {
 #pragma unroll
                     for (int e = 0; e < 8; ++e) val[e] = inside ? lrelu(val[e]) : 0.f;
@@ -431,14 +460,15 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
       }
     }
     // ---- MRF mean of this item
-    {
-      const int t = t0 + row_i;
+#pragma unroll
+    for (int o = 0; o < OBLK; ++o) {
+      const int t = t0 + 128 * o + row_i;
       if (t < T) {
 #pragma unroll
         for (int s = 0; s < SL; ++s) {
           float* op = p.out + (long long)b * bs + (long long)(16 * (grp * SL + s)) * T + t;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) st_streaming(op + (long long)i * T, (nrb > 1) ? racc[s][i] / p.div : racc[s][i]);
+          for (int i = 0; i < 16; ++i) st_streaming(op + (long long)i * T, (nrb > 1) ? racc[o][s][i] / p.div : racc[o][s][i]);
         }
       }
     }
