@@ -372,6 +372,50 @@ def run_ours(args):
     gen = torch.Generator(device=dev).manual_seed(4321 + rank)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if wl.get("flush_l2") else None
 
+    # ---- end-to-end leg, device -> host: the waveform of step i is copied to pinned host memory on a side stream while
+    # step i + 1 computes (what a serving loop does); at most one copy in flight, two host buffers, and the LAST copy is
+    # waited for inside the timed region (timed(..., drain=)), so every step's D2H is inside it.  The latency workload
+    # (L2 flushed between steps, per-step events) keeps the serial form: copy, then synchronize.
+    pipelined = flush_buf is None
+    copy_stream = torch.cuda.Stream(device=dev) if pipelined else None
+    d2h_state = {"bufs": [None, None], "i": 0, "pending": None}
+
+    def d2h_submit(outs):
+        n = sum(o_.numel() for o_ in outs)
+        k = d2h_state["i"] & 1
+        d2h_state["i"] += 1
+        if n and (d2h_state["bufs"][k] is None or d2h_state["bufs"][k].numel() < n):
+            d2h_state["bufs"][k] = torch.empty(int(n * 1.25) + 4096, dtype=torch.float32).pin_memory()   # flat: contiguous D2H
+        buf = d2h_state["bufs"][k]
+        if not pipelined:
+            off = 0
+            for o_ in outs:
+                buf[off:off + o_.numel()].copy_(o_.reshape(-1), non_blocking=True)
+                off += o_.numel()
+            torch.cuda.current_stream().synchronize()
+            return n * 4
+        computed = torch.cuda.Event()
+        computed.record()
+        if d2h_state["pending"] is not None:
+            d2h_state["pending"].synchronize()          # the previous step's copy (finished long ago: bounds host buffers to two)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(computed)
+            off = 0
+            for o_ in outs:
+                buf[off:off + o_.numel()].copy_(o_.reshape(-1), non_blocking=True)
+                o_.record_stream(copy_stream)
+                off += o_.numel()
+            done = torch.cuda.Event()
+            done.record(copy_stream)
+        d2h_state["pending"] = done
+        return n * 4
+
+    def d2h_drain():
+        if d2h_state["pending"] is not None:
+            torch.cuda.current_stream().wait_event(d2h_state["pending"])   # the end-of-region event is recorded after this
+            d2h_state["pending"].synchronize()
+            d2h_state["pending"] = None
+
     if kind == "generator":
         T = wl["frames"]
         zc = torch.randn(B, Cc, T, generator=torch.Generator().manual_seed(5678 + rank))
@@ -383,8 +427,7 @@ def run_ours(args):
         U = 1
         for u in hps.model.upsample_rates:
             U *= u
-        out_host = torch.empty(B * T * U, dtype=torch.float32).pin_memory()
-        h2d, d2h = z_host.numel() * 4, out_host.numel() * 4
+        h2d, d2h = z_host.numel() * 4, B * T * U * 4
 
         def step_resident():
             return net.dec(z_dev, g=g_dev)
@@ -392,8 +435,7 @@ def run_ours(args):
         def step_e2e():
             zz = z_host.to(dev, non_blocking=True)
             o_ = net.dec(zz, g=g_dev)
-            out_host.copy_(o_.reshape(-1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            d2h_submit([o_])
     else:
         seed_rank = 5678 if sharded or strong else 5678 + rank
         n_make = B_job if (sharded or strong) else B
@@ -426,7 +468,6 @@ def run_ours(args):
             noise_w = torch.randn(B, 2, x.shape[1], device=dev, generator=gen) if net.use_sdp else None
             infer_local(xd, ld, sdv, noise_w=noise_w)
             noise_z = torch.randn(B, Cc, state["Ty"], device=dev, generator=gen)
-        out_host = None
 
         def step_resident():
             if sharded:
@@ -440,7 +481,6 @@ def run_ours(args):
             return infer_local(xd, ld, sdv)
 
         def step_e2e():
-            nonlocal out_host
             if sharded:
                 a = xh.to(dev, non_blocking=True) if rank == 0 else None
                 b_ = lh.to(dev, non_blocking=True) if rank == 0 else None
@@ -451,20 +491,14 @@ def run_ours(args):
             else:
                 a, b_, c = xh.to(dev, non_blocking=True), lh.to(dev, non_blocking=True), sh.to(dev, non_blocking=True)
                 outs = infer_local(a, b_, c)                   # noise drawn on the device, as the reference does
-            n = sum(o_.numel() for o_ in outs)
-            if n and (out_host is None or out_host.numel() < n):
-                out_host = torch.empty(int(n * 1.25) + 4096, dtype=torch.float32).pin_memory()   # flat: contiguous D2H
-            off = 0
-            for o_ in outs:
-                out_host[off:off + o_.numel()].copy_(o_.reshape(-1), non_blocking=True)
-                off += o_.numel()
-            torch.cuda.current_stream().synchronize()
-            state["d2h"] = n * 4
+            state["d2h"] = d2h_submit(outs)
 
-    def timed(fn, steps):
+    def timed(fn, steps, drain=None):
         """EXACTLY `steps` steps between barrier + synchronize; device time from CUDA events on the launch stream
-        (per step, so an L2 flush between steps stays outside); returns (max over ranks, this rank's) ms."""
+        (per step, so an L2 flush between steps stays outside); `drain` (pipelined copies) runs before the closing event,
+        which is recorded after the launch stream has waited for the last copy; returns (max over ranks, this rank's) ms."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        ev_end = torch.cuda.Event(enable_timing=True)
         barrier()
         for i in range(steps):
             if flush_buf is not None:
@@ -472,8 +506,11 @@ def run_ours(args):
             ev[i][0].record()
             fn()
             ev[i][1].record()
+        if drain is not None:
+            drain()
+        ev_end.record()
         barrier()
-        ms = sum(a.elapsed_time(b) for a, b in ev) if flush_buf is not None else ev[0][0].elapsed_time(ev[-1][1])
+        ms = sum(a.elapsed_time(b) for a, b in ev) if flush_buf is not None else ev[0][0].elapsed_time(ev_end)
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if dist:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -499,7 +536,8 @@ def run_ours(args):
 
     for _ in range(2):
         step_e2e()
-    e2e_ms, _ = timed(step_e2e, args.steps)
+    d2h_drain()
+    e2e_ms, _ = timed(step_e2e, args.steps, drain=d2h_drain)
     if kind != "generator":
         d2h = state["d2h"] + 8
 
@@ -597,7 +635,9 @@ def run_ours(args):
             "rtf": 1.0 / value,
             "latency_ms_per_utterance": ms_per_step if B_job == 1 else None,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps,
+                    "d2h": "pipelined: step i's copy overlaps step i+1, last copy waited for inside the timed region" if pipelined
+                    else "serial: copy, then synchronize, every step"},
             "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(args.steps, 1),
             "clocks": clocks,
             "per_rank": [{"rank": i, "valid_frames": int(r[0]), "ms_per_step": r[1], "frames_max": int(r[2]),

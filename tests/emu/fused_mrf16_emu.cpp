@@ -152,6 +152,10 @@ int main(int argc, char** argv) {
   const int item = argc > 10 ? atoi(argv[10]) : 128;
 #define RUN(CC, TH, NBB, RPP, TW) return run<CC, TH, NBB, RPP, TW>(type, B, T, grid, nrb, la)
 #define RUN256(CC, TH, NBB, RPP, TW) return run<CC, TH, NBB, RPP, TW, 256>(type, B, T, grid, nrb, la)
+  if (item == 384) {
+    if (type == 2 && C == 32 && thr == 256 && ring == 6) return run<32, 256, 6, 481, false, 384>(type, B, T, grid, nrb, la);
+    return 64;
+  }
   if (item == 256) {
     // 256-sample work items (three M blocks per conv, two per resblock output)
     if (type == 2 && C == 32 && thr == 256 && ring == 6) RUN256(32, 256, 6, 353, false);

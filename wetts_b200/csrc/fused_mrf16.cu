@@ -104,12 +104,15 @@ int fused_mrf16_item_rows(int C, int type) {
   static const int c32 = getenv("WETTS_MRF16_ITEM_C32") ? atoi(getenv("WETTS_MRF16_ITEM_C32")) : 128;
   static const int c64 = getenv("WETTS_MRF16_ITEM_C64") ? atoi(getenv("WETTS_MRF16_ITEM_C64")) : 128;
   static const int rb1 = getenv("WETTS_MRF16_ITEM_RB1") ? atoi(getenv("WETTS_MRF16_ITEM_RB1")) : 128;
-  if (type == 2 && C == 32) return c32 == 256 ? 256 : 128;
+  if (type == 2 && C == 32) return (c32 == 256 || c32 == 384) ? c32 : 128;
   if (type == 2 && C == 64) return c64 == 256 ? 256 : 128;
   if (type == 1 && C == 32) return rb1 == 256 ? 256 : 128;
   return 128;
 }
-static int tile_pitch(int type, int item) { return item == 256 ? (type == 1 ? 377 : 353) : (type == 1 ? 249 : 225); }
+static int tile_pitch(int type, int item) {
+  if (item == 384) return 481;                     // ResBlock2, C = 32 only: four accumulator blocks = 256 TMEM columns
+  return item == 256 ? (type == 1 ? 377 : 353) : (type == 1 ? 249 : 225);
+}
 
 template <int C, int THREADS, int MINB, int NB, int RP, bool TWO, bool PROFILE, int ITEM = 128>
 static int launch_variant(const FusedMrfArgs& a, int grid, size_t smem, cudaStream_t s) {
@@ -139,6 +142,10 @@ template <bool PROFILE>
 static int launch_any(int C, int type, int ring, int per_sm, int item, const FusedMrfArgs& a, int grid, size_t smem, cudaStream_t s) {
 #define V(CC, TH, MB, NBB, RPP, TW) launch_variant<CC, TH, MB, NBB, RPP, TW, PROFILE>(a, grid, smem, s)
 #define V256(CC, TH, MB, NBB, RPP, TW) launch_variant<CC, TH, MB, NBB, RPP, TW, PROFILE, 256>(a, grid, smem, s)
+  if (item == 384) {
+    if (type == 2 && C == 32 && ring == 6) return launch_variant<32, 256, 2, 6, 481, false, PROFILE, 384>(a, grid, smem, s);
+    return 1;
+  }
   if (item == 256) {
     if (type == 2 && C == 32) return ring == 6 ? V256(32, 256, 2, 6, 353, false) : V256(32, 256, 2, 4, 353, false);
     if (type == 2 && C == 64) return ring == 6 ? V256(64, 512, 1, 6, 353, false) : V256(64, 512, 1, 4, 353, false);
@@ -207,10 +214,12 @@ int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
   if (smem > 227 * 1024) return 1;
   const long long items = (long long)a.B * ((a.T + item - 1) / item);   // upper bound in the length-aware mode
   // 256-sample items: three accumulator blocks -> 256 (C = 32) / 512 (C = 64) TMEM columns per CTA
-  const int per_sm = item == 256 ? ((C == 32 && a.type == 2) ? 2 : 1) : ctas_per_sm(C, a.type);
+  const int per_sm = item >= 256 ? ((C == 32 && a.type == 2) ? 2 : 1) : ctas_per_sm(C, a.type);
   static const int stagger = getenv("WETTS_MRF16_STAGGER") ? atoi(getenv("WETTS_MRF16_STAGGER")) : 0;
   a.stagger = per_sm > 1 ? stagger : 0;
   a.n_sm = n_sm;
+  static const int l2pf = getenv("WETTS_MRF16_L2PF") ? atoi(getenv("WETTS_MRF16_L2PF")) : 0;   // opt-in until measured
+  a.l2_prefetch = l2pf;
   const int grid = (int)(items < (long long)per_sm * n_sm ? items : (long long)per_sm * n_sm);
   if (getenv("WETTS_FUSED_RB_PROFILE")) return launch_profiled(C, a.type, ring, per_sm, item, a, grid, smem, items, s);
   return launch_any<false>(C, a.type, ring, per_sm, item, a, grid, smem, s);

@@ -49,7 +49,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   static_assert(C == 32 || C == 64 || C == 128, "channel count");
   static_assert(NB == 4 || NB == 6, "ring size");
   static_assert((RP & 1) == 1 && RP >= 225, "odd row pitch");
-  static_assert(ITEM == 128 || ITEM == 256, "output samples per work item");
+  static_assert(ITEM == 128 || ITEM == 256 || ITEM == 384, "output samples per work item");
   constexpr int OBLK = ITEM / 128;                              // M blocks of the last conv of a resblock (its output rows)
   constexpr int MBLK = OBLK + 1;                                // M blocks of any other conv (output + remaining halo <= 128 rows more)
   constexpr int N = C;
@@ -392,6 +392,14 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
         }
         // the next tile's input is requested while the tensor pipe works on the first conv of this resblock
         if (c == 0 && next_item >= 0) prefetch(next_item, next_j);
+        // variants without register prefetch (more staging units than threads): the warps that are idle during the MMAs
+        // warm L2 with the next ITEM's rows (widest halo), so its staging loads pay an L2 hit instead of a DRAM round trip
+        if (!PREFETCH && p.l2_prefetch && c == 0 && next_item >= 0 && next_item != item && warp >= 2) {
+          int b_n, t0_n;
+          decode(next_item, b_n, t0_n);
+          const int lo_n = t0_n - (RP - 1 - ITEM) / 2, hi_n = t0_n + ITEM + (RP - 1 - ITEM) / 2;
+          l2_prefetch_rows(p.in + (long long)b_n * bs, T, C, lo_n < 0 ? 0 : lo_n, hi_n > T ? T : hi_n, tid - 64, THREADS - 64);
+        }
         mark(2);
         mbar_wait(bar_acc, conv_count & 1);
         conv_count += 1;
