@@ -1,7 +1,7 @@
 // CPU check of fused_mrf16_kernel (wetts_b200/csrc/fused_mrf16_kernel.cuh) in the CTA emulator: the kernel source is
 // compiled for the host and compared with a direct fp64 evaluation of ResBlock1 / ResBlock2 x nrb + MRF mean
 // (decoders.py:157-170, :205-214, :72-76).
-//   usage: fused_mrf16_emu type C B T grid [nrb] [ring slots: 4 | 6] [threads] [length-aware: 0 | 1] [item rows: 128 | 256]
+//   usage: fused_mrf16_emu type C B T grid [nrb] [ring slots: 4 | 6] [threads] [length-aware: 0 | 1] [item rows: 128 | 256 | 384]
 #define WETTS_EMULATE 1
 #include <math.h>
 
@@ -154,6 +154,7 @@ int main(int argc, char** argv) {
 #define RUN256(CC, TH, NBB, RPP, TW) return run<CC, TH, NBB, RPP, TW, 256>(type, B, T, grid, nrb, la)
   if (item == 384) {
     if (type == 2 && C == 32 && thr == 256 && ring == 6) return run<32, 256, 6, 481, false, 384>(type, B, T, grid, nrb, la);
+    if (type == 2 && C == 32 && thr == 256 && ring == 4) return run<32, 256, 4, 481, false, 384>(type, B, T, grid, nrb, la);
     return 64;
   }
   if (item == 256) {

@@ -1418,7 +1418,7 @@ int wetts_generator_forward_view(wetts_vits_t h, const float* z, int64_t z_batch
           fa.bias[j][cc] = cv.b;
         }
       }
-      if (la) launch_mrf_item_map(la, B, len, len / T, kLaMargin, fused_mrf16_item_rows(ch, fa.type), w.item_map, &fa.item_map, &fa.n_items_dev, s);
+      if (la) launch_mrf_item_map(la, B, len, len / T, kLaMargin, fused_mrf16_item_rows(ch, fa.type, B, (int)len), w.item_map, &fa.item_map, &fa.n_items_dev, s);
       if (launch_fused_mrf16(ch, fa, s)) return fail("fused MRF (f16) launch failed");
       cur ^= 1;
       continue;

@@ -96,15 +96,26 @@ void launch_mrf_item_map(const long long* lengths, int B, int T, int rate, int m
   *n_items_dev = n_items;
 }
 
-// Output samples per work item (fused_mrf16_kernel's ITEM).  256-sample items amortise the halo (5 instead of 6 M blocks
-// per 256 samples of a ResBlock2 conv pair, 13 % fewer staged rows) at the price of three accumulator blocks in TMEM
-// (C = 32: 256 columns -> two CTAs per SM instead of three; C = 64: 512 columns -> one CTA per SM).
-// WETTS_MRF16_ITEM_C32 / _C64 / _RB1 = 128 | 256 override per kernel family (RB1: ResBlock1, C = 32 only).
-int fused_mrf16_item_rows(int C, int type) {
-  static const int c32 = getenv("WETTS_MRF16_ITEM_C32") ? atoi(getenv("WETTS_MRF16_ITEM_C32")) : 128;
+// Output samples per work item (fused_mrf16_kernel's ITEM).  Larger items amortise the halo: per 256 output samples a
+// ResBlock2 conv pair costs 6 M blocks with 128-sample items, 5 with 256, 4.67 with 384, and the staged rows drop by 13 /
+// 18 %; the price is one more accumulator block in TMEM per 128 samples (C = 32: 128 / 256 / 256 columns -> three / two / two
+// CTAs per SM; C = 64: 256 / 512 columns -> two / one CTA per SM).
+// Measured on one B200 (same box, two repeats each, profiles/r02w_*, r02x_*): C = 32 ResBlock2 with 384-sample items
+// -2.0 ms of generator time per step (53.3 -> 51.3 ms), 256-sample items -0.8 ms; C = 64 with 256-sample items (one CTA per
+// SM) +0.8 ms; ResBlock1 C = 32 with 256-sample items (one CTA per SM: 124 KB) +0.3 ms.  Hence: 384 for the C = 32
+// ResBlock2 stage when the launch has at least four items per CTA slot (a small launch -- B = 1 -- is latency bound and
+// keeps the short items: more CTAs busy, shorter critical path), 128 everywhere else.
+// WETTS_MRF16_ITEM_C32 / _C64 / _RB1 = 128 | 256 (| 384 for C32) force a size per kernel family (experiments).
+int fused_mrf16_item_rows(int C, int type, int B, int T) {
+  static const int c32 = getenv("WETTS_MRF16_ITEM_C32") ? atoi(getenv("WETTS_MRF16_ITEM_C32")) : 0;
   static const int c64 = getenv("WETTS_MRF16_ITEM_C64") ? atoi(getenv("WETTS_MRF16_ITEM_C64")) : 128;
   static const int rb1 = getenv("WETTS_MRF16_ITEM_RB1") ? atoi(getenv("WETTS_MRF16_ITEM_RB1")) : 128;
-  if (type == 2 && C == 32) return (c32 == 256 || c32 == 384) ? c32 : 128;
+  if (type == 2 && C == 32) {
+    if (c32 == 128 || c32 == 256 || c32 == 384) return c32;
+    const int n_sm = current_device_sm_count();
+    const long long n384 = (long long)B * ((T + 383) / 384);
+    return (n_sm > 0 && n384 >= 8LL * n_sm) ? 384 : 128;       // two CTAs per SM: >= 4 items per CTA slot
+  }
   if (type == 2 && C == 64) return c64 == 256 ? 256 : 128;
   if (type == 1 && C == 32) return rb1 == 256 ? 256 : 128;
   return 128;
@@ -143,7 +154,9 @@ static int launch_any(int C, int type, int ring, int per_sm, int item, const Fus
 #define V(CC, TH, MB, NBB, RPP, TW) launch_variant<CC, TH, MB, NBB, RPP, TW, PROFILE>(a, grid, smem, s)
 #define V256(CC, TH, MB, NBB, RPP, TW) launch_variant<CC, TH, MB, NBB, RPP, TW, PROFILE, 256>(a, grid, smem, s)
   if (item == 384) {
-    if (type == 2 && C == 32 && ring == 6) return launch_variant<32, 256, 2, 6, 481, false, PROFILE, 384>(a, grid, smem, s);
+    if (type == 2 && C == 32)
+      return ring == 6 ? launch_variant<32, 256, 2, 6, 481, false, PROFILE, 384>(a, grid, smem, s)
+                       : launch_variant<32, 256, 2, 4, 481, false, PROFILE, 384>(a, grid, smem, s);
     return 1;
   }
   if (item == 256) {
@@ -206,7 +219,7 @@ int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
   if (n_sm <= 0) return 1;
   const char* force = getenv("WETTS_FUSED_RB_RING");
   int ring = force ? atoi(force) : fused_mrf16_ring_slots(a.nq);
-  const int item = fused_mrf16_item_rows(C, a.type);
+  const int item = fused_mrf16_item_rows(C, a.type, a.B, a.T);
   const int rp = tile_pitch(a.type, item);
   if (ring == 6 && fused_mrf16_smem_bytes(C, 6, rp, a.type == 1 ? 2 : 1) > 227 * 1024) ring = 4;
   if (ring != 4 && !(ring == 6 && a.nq % 6 == 0)) return 1;

@@ -56,7 +56,7 @@ void launch_fused_mrf16_pack(const float* w_folded /*[C][C][K]*/, void* dst, int
 int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s);
 // length-aware work-item list of a stage (samples per frame `rate`, `margin` frames beyond each utterance's length)
 size_t mrf_item_map_bytes(int B, int T);
-int fused_mrf16_item_rows(int C, int type);   // output samples per work item of the stage kernel that will be launched
+int fused_mrf16_item_rows(int C, int type, int B, int T);   // output samples per work item of the stage kernel launch_fused_mrf16 will pick
 void launch_mrf_item_map(const long long* lengths, int B, int T, int rate, int margin, int item_rows, void* scratch,
                          const int2_t** item_map, const int** n_items_dev, cudaStream_t s);
 
