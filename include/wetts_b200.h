@@ -86,7 +86,11 @@ const char* wetts_version(void);
  * tcgen05 3xTF32 implicit-GEMM kernel (fp32-accurate), 0 forces the fp32 SIMT kernels.
  * "fused_resblock": 1 (default) runs each eligible HiFi-GAN stage (ResBlock2, 32 or 64 channels)
  * as ONE fused MRF kernel (both convs of every resblock + the mean on chip), 0 keeps one launch
- * per convolution.  Only effective with tensor_cores = 1. */
+ * per convolution.  Only effective with tensor_cores = 1.
+ * "mrf_item_rows": output samples per work item of the fused 32-channel ResBlock2 stage kernel:
+ * 0 (default) = chosen per launch (384 when the launch has >= 4 items per CTA slot, else 128),
+ * 128 / 256 / 384 = forced; every size computes bit-identical results.  Read-only
+ * "mrf_item_rows_last": the size the last such launch used. */
 int wetts_set_option(const char* name, int value);
 int wetts_get_option(const char* name, int* value);
 

@@ -99,3 +99,40 @@ def test_f16_path_against_oracle_random_ragged():
         net.set_option("tensor_format", 16)
         o = net.dec(z, g=net.emb_g(sid)[:, :, None])
         assert rel_rms_err(o.cpu(), ref) < GEN_TOL
+
+
+def test_work_item_sizes_of_the_c32_stage_are_bit_identical_and_match_the_oracle():
+    """The 32-channel ResBlock2 stage kernel picks 384-sample work items for large launches (what bench.py runs) and
+    128-sample items for small ones (what the fixture tests above run): every size must give the same bits, and the
+    large-launch route is checked against the CPU oracle directly (ragged against 128, 256 and 384)."""
+    import ctypes
+    import wetts_b200
+    from oracle import vits_oracle as O
+    from wetts_b200 import _lib, synth
+    from wetts_b200.hparams import builtin_config
+    lib = _lib.load()
+    hps = builtin_config("multilingual_v3")
+    sd = synth.make_state_dict(hps.model, 100, 2, seed=7)
+    gen = torch.Generator().manual_seed(321)
+    B, T = 8, 301                            # 8 x 77056 samples at the last stage: 1608 items of 384 >= 8 per SM
+    z = torch.randn(B, 192, T, generator=gen)
+    sid = torch.randint(0, 2, (B,), generator=gen)
+    net = wetts_b200.build_model(hps, 100, 2, sd, "cuda")
+    net.set_option("tensor_format", 16)
+    gv = net.emb_g(sid)[:, :, None]
+    last = ctypes.c_int(0)
+    outs = {}
+    try:
+        for rows in (0, 128, 256, 384):
+            _lib.check(lib.wetts_set_option(b"mrf_item_rows", rows))
+            outs[rows] = net.dec(z, g=gv).clone()
+            torch.cuda.synchronize()
+            _lib.check(lib.wetts_get_option(b"mrf_item_rows_last", ctypes.byref(last)))
+            assert last.value == (rows if rows else 384), f"requested {rows}, the launch used {last.value}"
+    finally:
+        _lib.check(lib.wetts_set_option(b"mrf_item_rows", 0))
+    for rows in (128, 256, 384):
+        assert torch.equal(outs[rows], outs[0]), f"{rows}-sample items differ from the default"
+    w = O.fold_weight_norm(sd)
+    ref = O.generator(w, hps.model, z[:2], w["emb_g.weight"][sid[:2]][:, :, None])
+    assert rel_rms_err(outs[0][:2].cpu(), ref) < GEN_TOL

@@ -497,6 +497,10 @@ int wetts_set_option(const char* name, int value) {
     g_attn_tc.store(value != 0);
     return 0;
   }
+  if (!strcmp(name, "mrf_item_rows")) {
+    if (set_mrf16_item_rows(value)) return fail("mrf_item_rows must be 0 (policy), 128, 256 or 384");
+    return 0;
+  }
   return fail("unknown option '%s'", name);
 }
 int wetts_get_option(const char* name, int* value) {
@@ -515,6 +519,14 @@ int wetts_get_option(const char* name, int* value) {
   }
   if (!strcmp(name, "attention_tensor_cores")) {
     *value = g_attn_tc.load();
+    return 0;
+  }
+  if (!strcmp(name, "mrf_item_rows")) {
+    *value = mrf16_item_rows_option();
+    return 0;
+  }
+  if (!strcmp(name, "mrf_item_rows_last")) {
+    *value = mrf16_last_item_rows();
     return 0;
   }
   return fail("unknown option '%s'", name);

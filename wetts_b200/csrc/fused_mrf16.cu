@@ -106,8 +106,20 @@ void launch_mrf_item_map(const long long* lengths, int B, int T, int rate, int m
 // ResBlock2 stage when the launch has at least four items per CTA slot (a small launch -- B = 1 -- is latency bound and
 // keeps the short items: more CTAs busy, shorter critical path), 128 everywhere else.
 // WETTS_MRF16_ITEM_C32 / _C64 / _RB1 = 128 | 256 (| 384 for C32) force a size per kernel family (experiments).
+// process-wide option "mrf_item_rows" (wetts_set_option): 0 = the policy above, 128 / 256 / 384 = that size for the C = 32
+// ResBlock2 stage (tests compare the sizes bit for bit); "mrf_item_rows_last" reads back what the last such launch used
+static std::atomic<int> g_item_opt{0}, g_item_last{0};
+int set_mrf16_item_rows(int rows) {
+  if (rows != 0 && rows != 128 && rows != 256 && rows != 384) return 1;
+  g_item_opt.store(rows);
+  return 0;
+}
+int mrf16_item_rows_option() { return g_item_opt.load(); }
+int mrf16_last_item_rows() { return g_item_last.load(); }
+
 int fused_mrf16_item_rows(int C, int type, int B, int T) {
-  static const int c32 = getenv("WETTS_MRF16_ITEM_C32") ? atoi(getenv("WETTS_MRF16_ITEM_C32")) : 0;
+  static const int c32_env = getenv("WETTS_MRF16_ITEM_C32") ? atoi(getenv("WETTS_MRF16_ITEM_C32")) : 0;
+  const int c32 = g_item_opt.load() ? g_item_opt.load() : c32_env;
   static const int c64 = getenv("WETTS_MRF16_ITEM_C64") ? atoi(getenv("WETTS_MRF16_ITEM_C64")) : 128;
   static const int rb1 = getenv("WETTS_MRF16_ITEM_RB1") ? atoi(getenv("WETTS_MRF16_ITEM_RB1")) : 128;
   if (type == 2 && C == 32) {
@@ -220,6 +232,7 @@ int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
   const char* force = getenv("WETTS_FUSED_RB_RING");
   int ring = force ? atoi(force) : fused_mrf16_ring_slots(a.nq);
   const int item = fused_mrf16_item_rows(C, a.type, a.B, a.T);
+  if (C == 32 && a.type == 2) g_item_last.store(item);
   const int rp = tile_pitch(a.type, item);
   if (ring == 6 && fused_mrf16_smem_bytes(C, 6, rp, a.type == 1 ? 2 : 1) > 227 * 1024) ring = 4;
   if (ring != 4 && !(ring == 6 && a.nq % 6 == 0)) return 1;

@@ -56,6 +56,9 @@ void launch_fused_mrf16_pack(const float* w_folded /*[C][C][K]*/, void* dst, int
 int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s);
 // length-aware work-item list of a stage (samples per frame `rate`, `margin` frames beyond each utterance's length)
 size_t mrf_item_map_bytes(int B, int T);
+int set_mrf16_item_rows(int rows);   // option "mrf_item_rows": 0 = policy, 128 / 256 / 384 forced (C = 32 ResBlock2 stage)
+int mrf16_item_rows_option();
+int mrf16_last_item_rows();
 int fused_mrf16_item_rows(int C, int type, int B, int T);   // output samples per work item of the stage kernel launch_fused_mrf16 will pick
 void launch_mrf_item_map(const long long* lengths, int B, int T, int rate, int margin, int item_rows, void* scratch,
                          const int2_t** item_map, const int** n_items_dev, cudaStream_t s);
