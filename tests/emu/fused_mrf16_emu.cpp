@@ -84,7 +84,6 @@ static int run(int type, int B, int T, int grid, int nrb, int len_aware) {
   }
   a.in = x.data(); a.out = out.data(); a.w = packed;
   a.smem_off = emu::kSmemBase;
-  a.stage_batch = getenv("EMU_STAGE_BATCH") ? atoi(getenv("EMU_STAGE_BATCH")) : 0;   // two-unit variants: both units' loads first
   // length-aware: utterance b computes only its first tiles (lengths 60 %, 100 %, 35 %, ... of T); the rest stays -777
   std::vector<int> prefix(B + 1, 0), ntile(B);
   const int n_tt = (T + ITEM - 1) / ITEM;

@@ -49,13 +49,6 @@ def test_fused_mrf16_kernel_in_emulator(emu_binary, case):
     assert "rel=" in r.stdout
 
 
-def test_fused_mrf16_batched_staging_in_emulator(emu_binary):
-    """C = 64 with 256 threads stages two units per thread without register prefetch; stage_batch issues both units' loads first"""
-    r = subprocess.run([emu_binary] + [str(v) for v in (2, 64, 2, 300, 2, 3, 6, 256, 0)], capture_output=True, text=True, timeout=900,
-                       env=dict(os.environ, EMU_STAGE_BATCH="1"))
-    assert r.returncode == 0, r.stdout + r.stderr
-
-
 # ---- the emulator must be able to FAIL on this kernel too
 MUTATIONS = {
     # the epilogue reads TMEM without waiting for the accumulator barrier -> stale accumulators

@@ -244,10 +244,6 @@ int launch_fused_mrf16(int C, FusedMrfArgs a, cudaStream_t s) {
   static const int stagger = getenv("WETTS_MRF16_STAGGER") ? atoi(getenv("WETTS_MRF16_STAGGER")) : 0;
   a.stagger = per_sm > 1 ? stagger : 0;
   a.n_sm = n_sm;
-  static const int l2pf = getenv("WETTS_MRF16_L2PF") ? atoi(getenv("WETTS_MRF16_L2PF")) : 0;   // opt-in until measured
-  a.l2_prefetch = l2pf;
-  static const int sbatch = getenv("WETTS_MRF16_STAGE_BATCH") ? atoi(getenv("WETTS_MRF16_STAGE_BATCH")) : 0;   // opt-in until measured
-  a.stage_batch = sbatch;
   const int grid = (int)(items < (long long)per_sm * n_sm ? items : (long long)per_sm * n_sm);
   if (getenv("WETTS_FUSED_RB_PROFILE")) return launch_profiled(C, a.type, ring, per_sm, item, a, grid, smem, items, s);
   return launch_any<false>(C, a.type, ring, per_sm, item, a, grid, smem, s);

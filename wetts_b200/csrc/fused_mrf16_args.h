@@ -41,8 +41,6 @@ struct FusedMrfArgs {
   // start-up stagger (cycles) of the k-th co-resident CTA of an SM (k = block index / n_sm): co-resident CTAs that
   // start together fall into a convoy (all in their MMA phase, then all in their SIMT phase); 0 = off
   int stagger = 0, n_sm = 1;
-  int stage_batch = 0;          // kernel variants that stage two units per thread without register prefetch: issue both units' loads first
-  int l2_prefetch = 0;          // kernel variants without register prefetch: warm L2 with the next item's rows during the MMAs
   long long* prof = nullptr;    // profiling instantiation only
 };
 

@@ -73,7 +73,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
   // (256-sample items: two units per thread are prefetched)
   constexpr int NU = (UNITS + STHREADS - 1) / STHREADS;
   constexpr bool PREFETCH = (NU == 1) || (ITEM > 128 && NU == 2);
-  constexpr int NPF = PREFETCH ? NU : (NU == 2 ? 2 : 1);    // unprefetched two-unit variants may batch both units' loads
+  constexpr int NPF = PREFETCH ? NU : 1;
   constexpr uint32_t A_HALF = (uint32_t)CG8 * RP * 16u;         // bytes of the hi (or lo') tile
   constexpr uint32_t TILE_BYTES = 2u * A_HALF;
   constexpr int NBIAS = kMrfMaxRb * kMrfMaxConv;
@@ -200,28 +200,6 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
     } else {
       int b, t0;
       decode(item, b, t0);
-      if (NU == 2 && p.stage_batch) {
-        // both units' loads (16 x 16 B per thread) in flight before the first conversion: one load round trip per
-        // staging phase instead of two
-        int cgs[2], qs[2];
-        bool on[2];
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int u = su + i * STHREADS;
-          cgs[i] = u & (CG8 - 1);
-          qs[i] = u >> LOG_CG8;
-          on[i] = (u < UNITS) && (qs[i] < Q);
-          const int t = t0 - Hp + 4 * qs[i];
-          const bool ok = on[i] && (t >= 0) && (t < T);
-          const float* src = p.in + (long long)b * bs + (long long)(8 * cgs[i]) * T + t;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) pf[i % NPF][e] = ok ? ldg4(src + (long long)e * T) : float4{0.f, 0.f, 0.f, 0.f};
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-          if (on[i]) store_unit(pf[i % NPF], cgs[i], qs[i]);
-        return;
-      }
 #pragma unroll 1
       for (int i = 0; i < NU; ++i) {
         const int u = su + i * STHREADS;
@@ -414,14 +392,6 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(THREADS, MINB) fused_mrf16_kernel(const Fu
         }
         // the next tile's input is requested while the tensor pipe works on the first conv of this resblock
         if (c == 0 && next_item >= 0) prefetch(next_item, next_j);
-        // variants without register prefetch (more staging units than threads): the warps that are idle during the MMAs
-        // warm L2 with the next ITEM's rows (widest halo), so its staging loads pay an L2 hit instead of a DRAM round trip
-        if (!PREFETCH && p.l2_prefetch && c == 0 && next_item >= 0 && next_item != item && warp >= 2) {
-          int b_n, t0_n;
-          decode(next_item, b_n, t0_n);
-          const int lo_n = t0_n - (RP - 1 - ITEM) / 2, hi_n = t0_n + ITEM + (RP - 1 - ITEM) / 2;
-          l2_prefetch_rows(p.in + (long long)b_n * bs, T, C, lo_n < 0 ? 0 : lo_n, hi_n > T ? T : hi_n, tid - 64, THREADS - 64);
-        }
         mark(2);
         mbar_wait(bar_acc, conv_count & 1);
         conv_count += 1;
