@@ -2,6 +2,7 @@
 // evaluation of the reference's windowed relative-position attention (attentions.py:232-282).
 //   usage: attn_tc_emu B T [len0 len1 ...]
 #define WETTS_EMULATE 1
+#include <stdlib.h>
 #include <math.h>
 
 #include <random>
@@ -28,7 +29,10 @@ int main(int argc, char** argv) {
   a.B = B; a.C = C; a.T = T; a.n_heads = H; a.window = W; a.smem_off = emu::kSmemBase;
   if (kAttnTcSmem > emu::kSmemBytes) { printf("smem over budget\n"); return 1; }
   unsigned long long n_mma = 0;
-  emu::launch(rel_attention_tc_kernel, a, B * H, kAttnTcThreads, &n_mma);
+  // EMU_ATTN_SHARED=1: the two-CTAs-per-SM variant (shared memory used twice, O in the TMEM columns of S)
+  const bool shared = getenv("EMU_ATTN_SHARED") && atoi(getenv("EMU_ATTN_SHARED"));
+  if (shared) emu::launch(rel_attention_tc_kernel<true>, a, B * H, kAttnTcThreads, &n_mma);
+  else emu::launch(rel_attention_tc_kernel<false>, a, B * H, kAttnTcThreads, &n_mma);
   double max_err = 0, sq = 0;
   const double scale = 1.0 / sqrt((double)DK);
   for (int b = 0; b < B; ++b)

@@ -88,10 +88,13 @@ def attn_emu_binary(tmp_path_factory):
 
 
 # (B, T, lengths...): full tile, ragged lengths incl. a nearly empty utterance (invalid query rows), short texts
+@pytest.mark.parametrize("shared", [0, 1])
 @pytest.mark.parametrize("case", [(2, 128, 128, 80), (3, 100, 100, 37, 1), (1, 64, 64), (2, 7, 7, 3)])
-def test_attention_tc_kernel_in_emulator(attn_emu_binary, case):
-    """windowed relative-position attention (attentions.py:232-282) on the emulated tensor pipe vs an fp64 evaluation"""
-    r = subprocess.run([attn_emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=600)
+def test_attention_tc_kernel_in_emulator(attn_emu_binary, case, shared):
+    """windowed relative-position attention (attentions.py:232-282) on the emulated tensor pipe vs an fp64 evaluation;
+    shared = 1: the two-CTAs-per-SM variant (shared memory used twice, O in the TMEM columns of S)"""
+    r = subprocess.run([attn_emu_binary] + [str(v) for v in case], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, EMU_ATTN_SHARED=str(shared)))
     assert r.returncode == 0, r.stdout + r.stderr
 
 

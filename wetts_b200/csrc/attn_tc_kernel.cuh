@@ -43,8 +43,16 @@ constexpr uint32_t kAttnKBytes = (kAttnTcDk / 8) * (2 * 128) * 16;      // 48 KB
 constexpr uint32_t kAttnPHalf = (kAttnTcMaxT / 8) * 128 * 16;           // 32 KB
 constexpr uint32_t kAttnVBytes = (kAttnTcMaxT / 8) * (2 * kAttnTcDk) * 16;   // 48 KB [Tk/8][hi ch | lo' ch][8]
 constexpr uint32_t kAttnTcSmem = 64 + 2 * kAttnQHalf + kAttnKBytes + 2 * kAttnPHalf + kAttnVBytes;
+// SHARED = two CTAs per SM: shared memory is used twice -- [q | k] (96 KB) for S = q k^T, then, q and k being dead once the S
+// MMAs have completed, [p (64 KB) | v (48 KB)] for O = p v -- and O reuses the TMEM columns of S: 112 KB and 256 columns per
+// CTA.  The kernel is a chain of latency-bound phases (staging, softmax from TMEM, epilogue) on four warps; a second
+// resident CTA is what fills the SM.
+constexpr uint32_t kAttnTcSmemShared = 64 + 2 * kAttnPHalf + kAttnVBytes;
+static_assert(2 * kAttnQHalf + kAttnKBytes <= 2 * kAttnPHalf + kAttnVBytes, "q | k must fit in the p | v region");
 
-WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kAttnTcThreads, 1) rel_attention_tc_kernel(const AttnTcArgs p) {
+template <bool SHARED>
+WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kAttnTcThreads, (SHARED ? 2 : 1)) rel_attention_tc_kernel(const AttnTcArgs p) {
+  constexpr uint32_t TMEM_COLS = SHARED ? 256u : 512u;
   using namespace tc;
   constexpr int DK = kAttnTcDk, TK = kAttnTcMaxT, W = 4, NREL = 2 * W + 1;
   WETTS_SMEM_DECL(smem);
@@ -59,11 +67,11 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kAttnTcThreads, 1) rel_attention_tc_kernel
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 32);
   uint8_t* Qs = smem + 64;
   uint8_t* Ks = Qs + 2 * kAttnQHalf;
-  uint8_t* Ps = Ks + kAttnKBytes;
-  uint8_t* Vs = Ps + 2 * kAttnPHalf;
+  uint8_t* Ps = SHARED ? smem + 64 : Ks + kAttnKBytes;   // SHARED: overlays q | k (written after the S MMAs have completed)
+  uint8_t* Vs = Ps + 2 * kAttnPHalf;                     // SHARED: overlays the tail of k (staged after the S MMAs)
   const uint32_t bar_s = smem_u32(&bars[0]), bar_o = smem_u32(&bars[1]);
   if ((smem_u32(smem) & 0xFFFFFFu) != p.smem_off) trap_now();     // same value in every thread: a uniform branch
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   if (tid == 0) {
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
@@ -96,20 +104,23 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kAttnTcThreads, 1) rel_attention_tc_kernel
     }
   }
   // ---- stage v^T: element (channel d, key j) at (j/8)*(2*DK*16) + d*16 + (j%8)*2 ; thread = (channel, 8-key group)
-  for (int u = tid; u < DK * (TK / 8); u += kAttnTcThreads) {
-    const int d = u % DK, jg = u / DK;
-    float v8[8];
+  auto stage_v = [&]() {
+    for (int u = tid; u < DK * (TK / 8); u += kAttnTcThreads) {
+      const int d = u % DK, jg = u / DK;
+      float v8[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = jg * 8 + e;
-      v8[e] = (j < T) ? ldg(vb + (long long)d * T + j) : 0.f;
+      for (int e = 0; e < 8; ++e) {
+        const int j = jg * 8 + e;
+        v8[e] = (j < T) ? ldg(vb + (long long)d * T + j) : 0.f;
+      }
+      uint4 hi, lo;
+      f16_split2(v8[0], v8[1], hi.x, lo.x); f16_split2(v8[2], v8[3], hi.y, lo.y);
+      f16_split2(v8[4], v8[5], hi.z, lo.z); f16_split2(v8[6], v8[7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(Vs + ((size_t)jg * (2 * DK) + d) * 16) = hi;
+      *reinterpret_cast<uint4*>(Vs + ((size_t)jg * (2 * DK) + DK + d) * 16) = lo;
     }
-    uint4 hi, lo;
-    f16_split2(v8[0], v8[1], hi.x, lo.x); f16_split2(v8[2], v8[3], hi.y, lo.y);
-    f16_split2(v8[4], v8[5], hi.z, lo.z); f16_split2(v8[6], v8[7], hi.w, lo.w);
-    *reinterpret_cast<uint4*>(Vs + ((size_t)jg * (2 * DK) + d) * 16) = hi;
-    *reinterpret_cast<uint4*>(Vs + ((size_t)jg * (2 * DK) + DK + d) * 16) = lo;
-  }
+  };
+  if (!SHARED) stage_v();
   fence_async_smem();
   tc_fence_before();
   cta_sync();
@@ -117,7 +128,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kAttnTcThreads, 1) rel_attention_tc_kernel
   const uint32_t tmem_base = uniform_bits(*tmem_slot, 5, 9);
 
   // ---- S = q k^T : accumulator columns [0, 128) main, [128, 256) small terms
-  constexpr uint32_t Q_OFF = 64u, K_OFF = Q_OFF + 2u * kAttnQHalf, P_OFF = K_OFF + kAttnKBytes, V_OFF = P_OFF + 2u * kAttnPHalf;
+  constexpr uint32_t Q_OFF = 64u, K_OFF = Q_OFF + 2u * kAttnQHalf, P_OFF = SHARED ? 64u : K_OFF + kAttnKBytes, V_OFF = P_OFF + 2u * kAttnPHalf;
   if (warp == 0) {
     const uint64_t qd = make_desc(p.smem_off + Q_OFF, 128u * 16u, 128u);
     const uint64_t kd = make_desc(p.smem_off + K_OFF, 256u * 16u, 128u);
@@ -146,6 +157,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kAttnTcThreads, 1) rel_attention_tc_kernel
   }
   mbar_wait(bar_s, 0);
   tc_fence_after();
+  if (SHARED) stage_v();   // every S MMA has completed: q and k are dead, their shared memory takes v and p
 
   // ---- masked softmax over the keys of row i, scores read from TMEM in 16-column slices (three passes)
   const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
@@ -214,8 +226,9 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kAttnTcThreads, 1) rel_attention_tc_kernel
   cta_sync();
   tc_fence_after();
 
-  // ---- O = p v : accumulator columns [256, 256+DK) main, [256+DK, 256+2DK) small terms
-  constexpr uint32_t O_COL = 256u;
+  // ---- O = p v : accumulator columns [O_COL, O_COL+DK) main, [O_COL+DK, O_COL+2DK) small terms (SHARED: the columns of S --
+  // every thread has read its scores for the last time before the CTA barrier above)
+  constexpr uint32_t O_COL = SHARED ? 0u : 256u;
   if (warp == 0) {
     const uint64_t pd = make_desc(p.smem_off + P_OFF, 128u * 16u, 128u);
     const uint64_t vd = make_desc(p.smem_off + V_OFF, (uint32_t)(2 * DK) * 16u, 128u);
@@ -250,7 +263,7 @@ WETTS_GLOBAL void WETTS_LAUNCH_BOUNDS(kAttnTcThreads, 1) rel_attention_tc_kernel
   }
   tc_fence_before();
   cta_sync();
-  if (warp == 0) tmem_dealloc(tmem_base, 512);
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 }  // namespace wetts
