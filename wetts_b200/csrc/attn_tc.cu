@@ -16,9 +16,10 @@ int launch_rel_attention_tc(const float* qkv, const float* emb_k, const float* e
   a.qkv = qkv; a.emb_k = emb_k; a.emb_v = emb_v; a.lengths = lengths; a.out = out;
   a.B = B; a.C = C; a.T = T; a.n_heads = n_heads; a.window = window;
   if (dyn_smem_offset(&a.smem_off, s)) return 1;
-  // two CTAs per SM (shared memory used twice, 256 TMEM columns): default since measured; WETTS_ATTN_TC_CTAS=1 = the
+  // two CTAs per SM (shared memory used twice, 256 TMEM columns): default since measured (240 -> 149 us per launch at the
+  // bench shape, profiles/r03d_*; Tx >= 64 fixtures green with it); WETTS_ATTN_TC_CTAS=1 = the
   // one-CTA layout (208 KB, 512 columns)
-  static const int ctas = getenv("WETTS_ATTN_TC_CTAS") ? atoi(getenv("WETTS_ATTN_TC_CTAS")) : 1;
+  static const int ctas = getenv("WETTS_ATTN_TC_CTAS") ? atoi(getenv("WETTS_ATTN_TC_CTAS")) : 2;
   if (ctas >= 2) {
     static DynSmemAttr attr2;
     if (attr2.ensure((const void*)rel_attention_tc_kernel<true>, kAttnTcSmemShared) != cudaSuccess) return 1;
