@@ -98,12 +98,15 @@ __device__ __forceinline__ void tc16_epilogue_slice(const ConvArgs& a, int b, in
       float* op = e.out + row + (size_t)co0 * Ts;
       float o[16];
       ld_strided<16>(e.resid + row + (size_t)co0 * Ts, step, nval, r);
+      // one code path for "accumulate" (acc_mode 1: dv = 1, x / 1 == x bit for bit) and "accumulate and average" (2): a
+      // three-way branch on acc_mode here made ptxas version the whole persistent loop and move the MMA descriptors through
+      // predicated R2UR.BROADCAST in this instantiation (170 R2UR, 20 UTCHMMA; now 60 / 14 like the other modes)
+      const float dv = (e.acc_mode == 2) ? e.div : 1.0f;
       if (e.acc_mode != 0) ld_strided<16>(op, step, nval, o);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         x[i] = v[i] + r[i];
-        if (e.acc_mode == 1) x[i] = o[i] + x[i];
-        else if (e.acc_mode == 2) x[i] = (o[i] + x[i]) / e.div;
+        if (e.acc_mode != 0) x[i] = (o[i] + x[i]) / dv;
       }
       st_strided<16>(op, step, nval, x);
       break;
@@ -240,12 +243,15 @@ __device__ __forceinline__ void tc16_epilogue_slice_r(const ConvArgs& a, int b, 
     case EPI_MRF: {
       float* op = e.out + row + (size_t)co0 * Ts;
       float o[16];
+      // one code path for "accumulate" (acc_mode 1: dv = 1, x / 1 == x bit for bit) and "accumulate and average" (2): a
+      // three-way branch on acc_mode here made ptxas version the whole persistent loop and move the MMA descriptors through
+      // predicated R2UR.BROADCAST in this instantiation (170 R2UR, 20 UTCHMMA; now 60 / 14 like the other modes)
+      const float dv = (e.acc_mode == 2) ? e.div : 1.0f;
       if (e.acc_mode != 0) ld_strided<16>(op, step, nval, o);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         x[i] = v[i] + r[i];
-        if (e.acc_mode == 1) x[i] = o[i] + x[i];
-        else if (e.acc_mode == 2) x[i] = (o[i] + x[i]) / e.div;
+        if (e.acc_mode != 0) x[i] = (o[i] + x[i]) / dv;
       }
       st_strided<16>(op, step, nval, x);
       break;
