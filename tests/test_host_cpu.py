@@ -90,3 +90,27 @@ def test_reference_loads_synthetic_checkpoint():
         hps = builtin_config(cfg)
         sd = synth.make_state_dict(hps.model, 40, 2, seed=3)
         ref_harness.build_reference_model(hps, 40, 2, sd)
+
+
+def test_mma_issue_paths_stay_in_the_uniform_datapath():
+    """DESIGN.md 4.5 as a test: in the built library no tcgen05.mma of a production kernel sits under a per-thread
+    predicate, and no vector -> uniform register move (R2UR) sits between the MMAs of an issue loop of the f16 kernels
+    (the EPI_MRF instantiation of the per-layer kernel once had 170 of them: found by eye, now found by this test)."""
+    import shutil
+    import sys
+    if not (shutil.which("cuobjdump") and shutil.which("c++filt")):
+        pytest.skip("cuobjdump / c++filt not available")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_issue_scan as S
+    from wetts_b200 import build
+    rows = [r for r in S.scan(build.build()) if not S.is_profiling(r["kernel"])]
+    names = " ".join(r["kernel"] for r in rows)
+    for must in ("fused_mrf16_kernel<32", "fused_mrf16_kernel<64", "conv1d_tc16_kernel<512, 1, 2>", "conv1d_tc16r_kernel<3, false>",
+                 "rel_attention_tc_kernel<true>"):
+        assert must in names, f"{must} not found in the library's SASS"
+    for r in rows:
+        assert r["per_thread_predicated_mmas"] == 0, r
+        if re.search(r"fused_mrf16_kernel|conv1d_tc16_kernel|conv1d_tc16r_kernel", r["kernel"]):
+            assert r["r2ur_between_mmas"] == 0, r
+        else:
+            assert r["r2ur_between_mmas"] <= 8, r     # 3xTF32 twins, attention (two issue regions)
