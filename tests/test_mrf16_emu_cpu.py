@@ -39,7 +39,7 @@ CASES = [(2, 32, 2, 300, 2, 3, 4, 256, 0), (2, 32, 1, 76, 1, 3, 6, 256, 0), (2, 
          (2, 64, 2, 600, 2, 3, 6, 512, 0, 256), (1, 32, 2, 600, 2, 3, 6, 256, 0, 256), (2, 32, 2, 512, 5, 1, 6, 256, 0, 256),
          # 384-sample items (the default of the C = 32 ResBlock2 stage for large launches: four M blocks = 256 TMEM columns)
          (2, 32, 2, 900, 2, 3, 6, 256, 0, 384), (2, 32, 4, 1000, 3, 3, 6, 256, 1, 384), (2, 32, 1, 76, 1, 3, 6, 256, 0, 384),
-         (2, 32, 2, 900, 2, 2, 4, 256, 0, 384)]
+         (2, 32, 2, 900, 2, 2, 4, 256, 0, 384), (2, 32, 1, 388, 2, 3, 6, 256, 0, 384), (2, 32, 2, 4, 3, 3, 6, 256, 0, 384)]
 
 
 @pytest.mark.parametrize("case", CASES)
